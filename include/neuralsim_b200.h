@@ -1,0 +1,179 @@
+/* neuralsim_b200 -- C ABI of the B200-native NeuS volume-rendering hot path.
+ *
+ * This header is the drop-in boundary: every entry point is what the reference's own
+ * native extensions (`nr3d_lib.bindings._lotd / _pack_ops / _occ_grid / _shencoder`, built by
+ * /root/reference/nr3d_lib/setup.py:134,184,239,516) expose to Python, restated as plain C: raw *device*
+ * pointers + sizes + a stream, no torch / ATen types.  The pybind11 / ctypes shim a maintainer would put on
+ * top is shown in INTEGRATION.md; `neuralsim_b200/bindings/*.py` is that shim over ctypes.
+ *
+ * Conventions
+ *   - all pointers are device pointers unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success, non-zero on failure; nsb_last_error() gives the message
+ *     (thread-local), mirroring the C++ exceptions -> RuntimeError behaviour of the reference;
+ *   - pack_infos is int64 [P,2] = (first, length), exactly the reference's layout
+ *     (csrc/pack_ops/pack_ops.h:11-65); packed_info of the marcher is int32 [R,2];
+ *   - fp16 tensors are IEEE binary16 (`__half`), passed as void* / uint16_t*.
+ */
+#ifndef NEURALSIM_B200_H
+#define NEURALSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_MAX_LEVELS 32
+#define NSB_MAX_DIMS 4
+
+/* lotd::LoDType values used on the path (csrc/lotd/include/lotd/lotd_types.h:16-26). */
+#define NSB_LOD_DENSE 0
+#define NSB_LOD_HASH 7
+
+/* Plain-C image of lotd::torch::LoDMeta (csrc/lotd/include/lotd/lotd_torch_api.h:143-200) restricted to
+ * Dense/Hash levels with linear interpolation -- the `c_hash_only` fast path of the reference. */
+typedef struct nsb_lotd_meta {
+    uint32_t n_dims_to_encode;
+    uint32_t n_levels;
+    uint32_t n_pseudo_levels;
+    uint32_t n_feat_per_pseudo_lvl;
+    uint32_t n_encoded_dims;
+    uint32_t n_params;
+    uint32_t level_res[NSB_MAX_LEVELS][NSB_MAX_DIMS];
+    uint32_t level_n_feats[NSB_MAX_LEVELS];
+    uint32_t level_types[NSB_MAX_LEVELS];
+    uint32_t level_sizes[NSB_MAX_LEVELS];
+    uint32_t level_offsets[NSB_MAX_LEVELS + 1];
+    uint32_t map_levels[NSB_MAX_LEVELS * 4];
+    uint32_t map_cnt[NSB_MAX_LEVELS * 4];
+} nsb_lotd_meta;
+
+const char *nsb_last_error(void);
+int nsb_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+uint64_t nsb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * _lotd  (csrc/lotd/src/lotd.cpp:22-107)
+ * ---------------------------------------------------------------------------------------------- */
+/* LoDMeta(n_input_dims, lod_res_multidim, lod_n_feats, lod_types, hashmap_size)   lotd_torch_api.cu:29-230
+ * lod_res_host: [n_levels * n_dims]; lod_types_host: NSB_LOD_* per level.  Host-only, no device work. */
+int nsb_lotd_meta_create(int32_t n_dims, int32_t n_levels, const int32_t *lod_res_host,
+                         const int32_t *lod_n_feats_host, const int32_t *lod_types_host,
+                         uint32_t hashmap_size, nsb_lotd_meta *out_host);
+
+/* lod_fwd(meta, input[N,D] f32 in [0,1], params f16|f32, max_level, need_input_grad)
+ *   -> y[N,F] (params dtype, row-major), dy_dx[N,F,D] f32 or NULL            lotd_torch_api.cu:232-365
+ * `input` must already be clamped to [1e-6, 1-1e-6] (the reference clamps in lotd.py:60). */
+int nsb_lotd_fwd(const nsb_lotd_meta *meta_host, const float *input, const void *params, int params_is_half,
+                 int64_t n, int32_t max_level, void *y, float *dy_dx, void *stream);
+
+/* lod_bwd, parameter part: dL_dparam[P] (fp32, accumulated -- caller zero-fills) += scatter(dL_dy * w)
+ *                                                                           lotd_hash_only.h:380-470
+ * dL_dy is [N,F] in the params dtype.  `scale` multiplies every contribution (the reference's
+ * 1/loss_scale, lotd.py:105). */
+int nsb_lotd_bwd_grid(const nsb_lotd_meta *meta_host, const void *dL_dy, int dL_dy_is_half, const float *input,
+                      int64_t n, int32_t max_level, float scale, float *dL_dparam, void *stream);
+
+/* lod_bwd, input part: dL_dx[N,D] = sum_f float(dL_dy[N,f]) * dy_dx[N,f,D]     lotd_hash_only.h:839-856 */
+int nsb_lotd_bwd_input(const void *dL_dy, int dL_dy_is_half, const float *dy_dx, int64_t n, int32_t n_feat,
+                       int32_t n_dims, float scale, float *dL_dx, void *stream);
+
+/* lod_bwd_bwd_input                                                         lotd_hash_only.h:951-1056
+ *   dL_ddLdy[N,F] f32 (may be NULL) = sum_d dL_ddLdx[N,d] * dy_dx[N,f,d]
+ *   dL_dparam[P] f32 (may be NULL, accumulated) += 2nd-order scatter of dL_ddLdx (x) dL_dy
+ * dy_dx may be NULL when dL_ddLdy is NULL. */
+int nsb_lotd_bwd_bwd_input(const nsb_lotd_meta *meta_host, const float *dL_ddLdx, const void *dL_dy,
+                           int dL_dy_is_half, const float *input, const float *dy_dx, int64_t n,
+                           int32_t max_level, float scale, float *dL_ddLdy, float *dL_dparam, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * _occ_grid  (csrc/occ_grid/src/occ_grid.cpp:21-33, include/occ_grid/cpp_api.h:14-65)
+ * ray_marching / batched_ray_marching, AABB contraction.  Two calls, as the reference's two kernel
+ * rounds (ray_marching.cu:179-241): first with packed_info == NULL to fill num_steps[R]; the caller
+ * builds packed_info = (exclusive cumsum, num_steps) and calls again to fill the sample arrays.
+ * batch_inds == NULL -> single grid bool[rx,ry,rz], roi[6]; else grid bool[B,rx,ry,rz], roi[B,6].
+ * ---------------------------------------------------------------------------------------------- */
+int nsb_ray_marching(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min,
+                     const float *t_max, const float *roi, const int32_t *batch_inds, int32_t rx, int32_t ry,
+                     int32_t rz, const uint8_t *grid_binary, float step_size, float max_step_size,
+                     float dt_gamma, uint32_t max_steps, const int32_t *packed_info, int32_t *num_steps,
+                     float *t_starts, float *t_ends, int32_t *ridx, int32_t *gidx, int32_t *bidx, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * _pack_ops  (csrc/pack_ops/pack_ops.cpp:20-58, pack_ops.h:11-65).  fp32 features unless noted.
+ * ---------------------------------------------------------------------------------------------- */
+enum { NSB_OP_ADD = 0, NSB_OP_SUB, NSB_OP_MUL, NSB_OP_DIV, NSB_OP_GT, NSB_OP_GEQ, NSB_OP_LT, NSB_OP_LEQ,
+       NSB_OP_EQ, NSB_OP_NEQ };
+/* packed_{add,sub,mul,div}: out[i,c] = feats[i,c] (op) other[pack(i),c]; compare ops write uint8. */
+int nsb_packed_binary(int op, const float *feats, const float *other, const int64_t *pack_infos, int64_t n_packs,
+                      int32_t feat_dim, void *out, void *stream);
+int nsb_packed_sum(const float *feats, const int64_t *pack_infos, int64_t n_packs, int32_t feat_dim, float *out,
+                   void *stream);
+int nsb_packed_cumsum(const float *feats, const int64_t *pack_infos, int64_t n_packs, int32_t feat_dim,
+                      int exclusive, int reverse, float *out, void *stream);
+/* packed_diff / packed_backward_diff with optional per-pack appends|last_fill / prepends|first_fill. */
+int nsb_packed_diff(const float *feats, const int64_t *pack_infos, int64_t n_packs, int32_t feat_dim,
+                    const float *appends, const float *last_fill, int backward, float *out, void *stream);
+int nsb_packed_searchsorted(const float *bins, const float *vals, const int64_t *pack_infos, int64_t n_packs,
+                            int32_t n_vals, int64_t *out_idx, void *stream);
+int nsb_packed_invert_cdf(const float *bins, const float *cdfs, const float *u, const int64_t *pack_infos,
+                          int64_t n_packs, int32_t n_samples, float *samples, int64_t *bin_idx, void *stream);
+/* try_merge_two_packs_sorted_aligned: pack_infos_out [P,2] must hold (first,len) of the merged packs. */
+int nsb_merge_two_packs_sorted_aligned(const float *vals_a, const int64_t *pack_infos_a, const float *vals_b,
+                                       const int64_t *pack_infos_b, const int64_t *pack_infos_out,
+                                       int64_t n_packs, int b_sorted, int64_t *pidx_a, int64_t *pidx_b,
+                                       void *stream);
+/* packed_alpha_to_vw_forward: weights (may be NULL), num_steps int64[P] + selector uint8[S] (may be NULL). */
+int nsb_packed_alpha_to_vw_forward(const float *alphas, const int64_t *pack_infos, int64_t n_packs,
+                                   float early_stop_eps, float alpha_thre, float *weights, int64_t *num_steps,
+                                   uint8_t *selector, void *stream);
+int nsb_packed_alpha_to_vw_backward(const float *weights, const float *grad_weights, const float *alphas,
+                                    const int64_t *pack_infos, int64_t n_packs, float early_stop_eps,
+                                    float alpha_thre, float *grad_alphas, void *stream);
+/* interleave_arange / interleave_linstep: cumsum_steps is the inclusive cumsum of num_steps (int64[P]). */
+int nsb_interleave_linstep(const float *start, const int64_t *num_steps, const int64_t *cumsum_steps,
+                           const float *step_size, float step_scalar, int64_t n_packs, float *out, int64_t *nidx,
+                           void *stream);
+int nsb_interleave_arange(const int64_t *num_steps, const int64_t *cumsum_steps, int64_t n_packs, int64_t *out,
+                          int64_t *nidx, void *stream);
+/* packed_sort_qsort: ascending, in place on vals; idx (may be NULL) receives global gather indices. */
+int nsb_packed_sort(float *vals, const int64_t *pack_infos, int64_t n_packs, int64_t *idx, void *stream);
+int nsb_mark_pack_boundaries(const int64_t *ids, int64_t n, int32_t *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * _shencoder  (externals/shencoder/bindings.cpp, shencoder.h): real SH basis, degree C in [1,4].
+ * ---------------------------------------------------------------------------------------------- */
+int nsb_sh_encode_forward(const float *inputs, float *outputs, int64_t n, int32_t degree, float *dy_dx,
+                          void *stream);
+int nsb_sh_encode_backward(const float *grad, const float *dy_dx, int64_t n, int32_t degree, float *grad_inputs,
+                           void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused entry points (the coarser L2->L1 boundary of SURVEY.md §8b "Fused boundary we add").
+ * They replace chains of the calls above + the autocast MLPs of nr3d_lib/models/blocks/mlp.py with one
+ * kernel each; numerics follow the same fp16 rounding points (see DESIGN.md "Numerics contract").
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nsb_sdf_decoder {       /* LoTDSDF decoder 32->W->1, Softplus(beta)  (lotd_sdf.py:176-200) */
+    const void *W1;                    /* fp16 [W, F]   (fp32 master rounded by the caller) */
+    const void *b1;                    /* fp16 [W] */
+    const void *W2;                    /* fp16 [W] */
+    const void *b2;                    /* fp16 [1] */
+    int32_t width;                     /* W (<= 64, multiple of 16) */
+    float beta;                        /* 100 */
+} nsb_sdf_decoder;
+
+/* forward_sdf on N points: x in network space [-1,1]^3 (not yet /2+0.5).  sdf fp32 (fp16-valued). */
+int nsb_fused_sdf(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host,
+                  const float *x, int64_t n, int32_t max_level, float *sdf, void *h_out_half, void *stream);
+
+/* x = o[ridx] + d[ridx] * t, then forward_sdf.  ridx int64[N] indexes rays_o / rays_d [R,3]. */
+int nsb_fused_sdf_rays(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host,
+                       const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
+                       int32_t max_level, float *sdf, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURALSIM_B200_H */

@@ -1,0 +1,96 @@
+"""ctypes loader of libneuralsim_b200.so (the C ABI of include/neuralsim_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a tensor is not a contiguous CUDA tensor of the
+expected dtype, the call raises.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libneuralsim_b200.so")
+
+NSB_MAX_LEVELS, NSB_MAX_DIMS = 32, 4
+LOD_DENSE, LOD_HASH = 0, 7
+
+
+class LotdMetaC(ctypes.Structure):
+    _fields_ = [
+        ("n_dims_to_encode", ctypes.c_uint32), ("n_levels", ctypes.c_uint32), ("n_pseudo_levels", ctypes.c_uint32),
+        ("n_feat_per_pseudo_lvl", ctypes.c_uint32), ("n_encoded_dims", ctypes.c_uint32), ("n_params", ctypes.c_uint32),
+        ("level_res", (ctypes.c_uint32 * NSB_MAX_DIMS) * NSB_MAX_LEVELS),
+        ("level_n_feats", ctypes.c_uint32 * NSB_MAX_LEVELS), ("level_types", ctypes.c_uint32 * NSB_MAX_LEVELS),
+        ("level_sizes", ctypes.c_uint32 * NSB_MAX_LEVELS), ("level_offsets", ctypes.c_uint32 * (NSB_MAX_LEVELS + 1)),
+        ("map_levels", ctypes.c_uint32 * (NSB_MAX_LEVELS * 4)), ("map_cnt", ctypes.c_uint32 * (NSB_MAX_LEVELS * 4)),
+    ]
+
+
+class SdfDecoderC(ctypes.Structure):
+    _fields_ = [("W1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("W2", ctypes.c_void_p), ("b2", ctypes.c_void_p),
+                ("width", ctypes.c_int32), ("beta", ctypes.c_float)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"neuralsim_b200: {LIB_PATH} is missing. Build it with `python -m neuralsim_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback for this package.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.nsb_last_error.restype = ctypes.c_char_p
+        _lib.nsb_launch_count.restype = ctypes.c_uint64
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().nsb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what}: {msg}" if what else msg)
+
+
+def launch_count() -> int:
+    return int(lib().nsb_launch_count())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_DT = {"f32": torch.float32, "f16": torch.float16, "i64": torch.int64, "i32": torch.int32, "u8": torch.uint8,
+       "bool": torch.bool}
+
+
+def ptr(t, dtype=None, name="tensor", allow_none=False):
+    """Device pointer of a contiguous CUDA tensor (raises otherwise)."""
+    if t is None:
+        if allow_none:
+            return ctypes.c_void_p(0)
+        raise RuntimeError(f"{name} must not be None")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (neuralsim_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None:
+        want = _DT[dtype] if isinstance(dtype, str) else dtype
+        if t.dtype != want:
+            raise RuntimeError(f"{name} must have dtype {want}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def c_i64(v):
+    return ctypes.c_int64(int(v))
+
+
+def c_i32(v):
+    return ctypes.c_int32(int(v))
+
+
+def c_f32(v):
+    return ctypes.c_float(float(v))

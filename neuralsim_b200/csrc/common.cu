@@ -1,0 +1,20 @@
+// Error channel, version and launch counter of the neuralsim_b200 C ABI.
+#include <stdarg.h>
+
+#include "nsb_common.cuh"
+
+namespace nsb {
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace nsb
+
+extern "C" const char *nsb_last_error(void) { return nsb::g_err; }
+extern "C" int nsb_version(void) { return 100; }
+extern "C" uint64_t nsb_launch_count(void) { return nsb::g_launches.load(); }

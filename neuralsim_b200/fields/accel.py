@@ -1,0 +1,164 @@
+"""Occupancy-grid acceleration -- API of `nr3d_lib.models.accelerations.OccGridEma / OccGridAccel`
+(reference: models/accelerations/occgrid/ema_single.py:21-260, occgrid/utils.py:17-109, occgrid_accel/single.py:36-135).
+torch_scatter's `scatter_max(out=decay*grid)` is `Tensor.scatter_reduce_('amax', include_self=True)` here."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..graphics.raymarch import occgrid_raymarch
+
+
+def sample_pts_in_voxels(gidx, num_pts, resolution, dtype=torch.float, generator=None):
+    """Uniform points in [-1,1]^3 inside the listed voxels (+ the voxel each one fell in)  (utils.py:17-41)."""
+    device, nv = gidx.device, gidx.shape[0]
+    if num_pts / nv < 2.0:
+        vidx = torch.randint(nv, [num_pts], device=device, generator=generator)
+        off = torch.rand([num_pts, 3], device=device, dtype=dtype, generator=generator)
+        return ((gidx[vidx] + off) / resolution.float()) * 2 - 1, vidx
+    per = int(num_pts // nv) + 1
+    off = torch.rand([nv, per, 3], device=device, dtype=dtype, generator=generator)
+    pts = ((gidx[:, None, :] + off) / resolution.float()).view(-1, 3) * 2 - 1
+    return pts, torch.arange(nv, device=device).unsqueeze(-1).expand(nv, per).reshape(-1)
+
+
+def sdf_to_occ_val(sdf, inv_s):
+    """normalised logistic density: 4 s (1 - s), s = sigmoid(sdf * inv_s)   (maths: normalized_logistic_density)."""
+    s = torch.sigmoid(sdf * inv_s)
+    return 4. * s * (1. - s)
+
+
+class OccGridEma(nn.Module):
+    def __init__(self, resolution=(64, 64, 64), occ_val_fn_cfg=dict(type="sdf", inv_s=256.0), occ_thre=0.3, ema_decay=0.95,
+                 init_cfg=dict(mode="from_net", num_steps=4, num_pts=2 ** 20), update_from_net_cfg=dict(num_steps=4, num_pts=2 ** 20),
+                 update_from_samples_cfg=dict(), n_steps_between_update=16, n_steps_warmup=256, dtype=torch.float, device=None):
+        super().__init__()
+        res = torch.tensor([resolution] * 3 if isinstance(resolution, int) else list(resolution), dtype=torch.int32, device=device)
+        self.register_buffer("is_initialized", torch.tensor([False], dtype=torch.bool, device=device), persistent=True)
+        self.register_buffer("resolution", res, persistent=False)
+        self.register_buffer("occ_grid", torch.zeros(res.tolist(), dtype=torch.bool, device=device), persistent=True)
+        self.register_buffer("occ_val_grid", torch.zeros(res.tolist(), dtype=dtype, device=device), persistent=True)
+        g = torch.stack(torch.meshgrid([torch.arange(r, device=device) for r in res.tolist()], indexing="ij"), -1).view(-1, 3)
+        self.register_buffer("gidx_full", g, persistent=False)
+        if occ_val_fn_cfg.get("type", "sdf") != "sdf":
+            raise RuntimeError("only occ_val_fn type 'sdf' is built")
+        self.occ_inv_s = float(occ_val_fn_cfg["inv_s"])
+        self.occ_thre, self.ema_decay = occ_thre, ema_decay
+        self.init_cfg, self.update_from_net_cfg = dict(init_cfg), dict(update_from_net_cfg)
+        self.should_collect_samples = update_from_samples_cfg is not None
+        self.n_steps_between_update, self.n_steps_warmup = n_steps_between_update, n_steps_warmup
+        if self.should_collect_samples:
+            self.register_buffer("_occ_val_grid_pcl", torch.zeros(res.tolist(), dtype=dtype, device=device), persistent=False)
+
+    def occ_val_fn(self, sdf):
+        return sdf_to_occ_val(sdf.float(), self.occ_inv_s)
+
+    def _ravel(self, gidx):
+        r = self.occ_val_grid.shape
+        return (gidx * gidx.new_tensor([r[1] * r[2], r[2], 1])).sum(-1)
+
+    def _gidx_of(self, pts):
+        return ((pts / 2. + 0.5) * self.resolution).long().clamp(self.resolution.new_tensor([0]), self.resolution - 1)
+
+    @torch.no_grad()
+    def _update(self, gidx, occ_val, ema_decay):
+        """EMA-decay every voxel, take the max with the new evidence, write back only the touched voxels (utils.py:89-101)."""
+        flat = self._ravel(gidx)
+        new = (ema_decay * self.occ_val_grid.flatten()).scatter_reduce_(0, flat, occ_val.flatten().to(self.occ_val_grid), "amax", include_self=True)
+        self.occ_val_grid.view(-1)[flat] = new[flat]
+        self.occ_grid = self.occ_val_grid > self.occ_thre
+
+    @torch.no_grad()
+    def set_occ_grid(self, occ_grid):
+        self.occ_grid = occ_grid.to(self.occ_grid.device).bool().contiguous()
+        self.occ_val_grid = self.occ_grid.to(self.occ_val_grid.dtype)
+        self.is_initialized.fill_(True)
+
+    @torch.no_grad()
+    def init(self, val_query_fn=None, logger=None, generator=None):
+        if bool(self.is_initialized):
+            return False
+        cfg = dict(self.init_cfg)
+        mode = cfg.pop("mode")
+        if mode == "constant":
+            self.occ_val_grid.fill_(cfg["constant_value"])
+            self.occ_grid = self.occ_val_grid > self.occ_thre
+        elif mode == "from_net":
+            for _ in range(cfg.get("num_steps", 4)):
+                empty = self.occ_grid.logical_not().nonzero().long()
+                if empty.shape[0] > 0:
+                    pts = sample_pts_in_voxels(empty, cfg.get("num_pts", 2 ** 18), self.resolution, self.occ_val_grid.dtype, generator)[0]
+                    self._update(self._gidx_of(pts), self.occ_val_fn(val_query_fn(pts)), 1.0)
+        else:
+            raise RuntimeError(f"Invalid init_mode={mode}")
+        self.is_initialized.fill_(True)
+        return True
+
+    @torch.no_grad()
+    def step(self, cur_it, val_query_fn, logger=None, generator=None):
+        assert bool(self.is_initialized), "init() first"
+        if cur_it <= 0 or cur_it % self.n_steps_between_update != 0:
+            return False
+        num_steps, num_pts = self.update_from_net_cfg.get("num_steps", 4), self.update_from_net_cfg.get("num_pts", 2 ** 18)
+        dt = self.occ_val_grid.dtype
+        pts_all, val_all = [], []
+        occupied, empty = self.occ_grid.nonzero().long(), self.occ_grid.logical_not().nonzero().long()
+        for _ in range(num_steps):
+            if cur_it < self.n_steps_warmup:
+                pts = sample_pts_in_voxels(self.gidx_full, num_pts, self.resolution, dt, generator)[0]
+            else:
+                assert occupied.numel() > 0, "Occupancy grid becomes empty during training."
+                parts = [sample_pts_in_voxels(self.gidx_full, num_pts // 2, self.resolution, dt, generator)[0]]
+                if empty.numel() > 0:
+                    parts.append(sample_pts_in_voxels(empty, num_pts // 4, self.resolution, dt, generator)[0])
+                parts.append(sample_pts_in_voxels(occupied, num_pts // 4, self.resolution, dt, generator)[0])
+                pts = torch.cat(parts, 0)
+            pts_all.append(pts)
+            val_all.append(val_query_fn(pts))
+        pts, occ_val = torch.cat(pts_all, 0), self.occ_val_fn(torch.cat(val_all, 0).flatten())
+        gidx = self._gidx_of(pts)
+        if self.should_collect_samples:
+            idx = self._occ_val_grid_pcl.nonzero().long()
+            if idx.numel() > 0:
+                gidx = torch.cat([gidx, idx], 0)
+                occ_val = torch.cat([occ_val, self._occ_val_grid_pcl[tuple(idx.t())]], 0)
+            self._occ_val_grid_pcl.zero_()
+        self._update(gidx, occ_val, self.ema_decay)
+        return True
+
+    @torch.no_grad()
+    def collect_samples(self, pts, val=None):
+        """Max-accumulate the occupancy evidence of points seen during rendering (ema_single.py:213-240)."""
+        if self.training and self.should_collect_samples and val is not None:
+            flat = self._ravel(self._gidx_of(pts.flatten(0, -2)))
+            self._occ_val_grid_pcl.view(-1).scatter_reduce_(0, flat, self.occ_val_fn(val.flatten()).to(self._occ_val_grid_pcl), "amax", include_self=True)
+
+    @torch.no_grad()
+    def sample_pts_in_occupied(self, num_pts, generator=None):
+        return sample_pts_in_voxels(self.occ_grid.nonzero().long(), num_pts, self.resolution, self.occ_val_grid.dtype, generator)[0]
+
+
+class OccGridAccel(nn.Module):
+    """Single-block occupancy-grid accelerator: `occ` (the EMA grid) + `ray_march` (occgrid_accel/single.py:36-135)."""
+
+    def __init__(self, space=None, device=None, **occ_cfg):
+        super().__init__()
+        occ_cfg.pop("type", None)
+        self.space = space
+        self.occ = OccGridEma(**occ_cfg, device=device)
+        self.training_granularity = 0.0
+
+    def init(self, query_fn, logger=None):
+        return self.occ.init(query_fn, logger)
+
+    def step(self, cur_it, query_fn, logger=None):
+        return self.occ.step(cur_it, query_fn, logger)
+
+    def collect_samples(self, pts, val=None):
+        self.occ.collect_samples(pts, val)
+
+    def sample_pts_in_occupied(self, num_pts):
+        return self.occ.sample_pts_in_occupied(num_pts)
+
+    def ray_march(self, rays_o, rays_d, near=None, far=None, perturb=False, **march_cfg):
+        return occgrid_raymarch(self.occ.occ_grid, rays_o, rays_d, near, far, perturb=perturb, **march_cfg)

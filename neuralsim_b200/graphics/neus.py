@@ -1,0 +1,231 @@
+"""NeuS maths and the per-ray query -- API of `nr3d_lib.graphics.neus`
+(reference: nr3d_lib/nr3d_lib/graphics/neus/neus_utils.py, neus_ray_query.py:732-1104).
+
+`neus_ray_query_march_occ_multi_upsample_compressed(model, ray_tested, ...)` is the hot path's entry point: the
+function `NeusRendererMixin.ray_query` dispatches to for `query_mode: march_occ_multi_upsample_compressed`
+(renderer_mixin.py:346-350).  It returns the same packed `volume_buffer` dict (renderer_mixin.py:263-303).
+Duck-typed `model` interface: forward_sdf(x)->{'sdf'}, forward(x, v=, h_appear=, nablas_has_grad=, with_rgb=,
+with_normal=)->{'sdf','nablas','rgb','h'}, forward_inv_s(), accel.ray_march(rays_o, rays_d, near=, far=, perturb=, **march_cfg).
+"""
+from __future__ import annotations
+
+from operator import itemgetter
+
+import torch
+import torch.nn.functional as F
+
+from .nerf import packed_alpha_to_vw, packed_volume_render_compression, ray_alpha_to_vw
+from .pack_ops import (get_pack_infos_from_batch, merge_two_batch_a_includes_b, merge_two_packs_sorted_aligned,
+                       packed_cumsum, packed_diff, packed_div)
+from .raysample import batch_sample_step_linear, packed_sample_cdf
+
+__all__ = ["neus_cdf", "neus_ray_cdf_to_alpha", "neus_ray_sdf_to_alpha", "neus_ray_sdf_to_vw", "neus_packed_cdf_to_alpha",
+           "neus_packed_sdf_to_alpha", "neus_packed_sdf_to_upsample_alpha", "neus_ray_sdf_to_upsample_alpha",
+           "neus_ray_query_march_occ_multi_upsample_compressed"]
+
+
+def neus_cdf(x, inv_s):
+    return torch.sigmoid(x * inv_s)
+
+
+# ---- batched rays [..., n+1] boundary values -> [..., n] interval alphas
+def neus_ray_cdf_to_alpha(cdf, append_cdf_1=False):
+    if append_cdf_1:
+        d = cdf.diff(append=cdf.new_full((*cdf.shape[:-1], 1), 1.))
+        return (-d / (cdf + 1e-5)).clamp_min(0)
+    return (-cdf.diff() / (cdf[..., :-1] + 1e-5)).clamp_min(0)
+
+
+def neus_ray_sdf_to_alpha(sdf, inv_s, append_cdf_1=False):
+    return neus_ray_cdf_to_alpha(torch.sigmoid(sdf * inv_s), append_cdf_1)
+
+
+def neus_ray_sdf_to_vw(sdf, inv_s, append_cdf_1=False):
+    return ray_alpha_to_vw(neus_ray_sdf_to_alpha(sdf, inv_s, append_cdf_1))
+
+
+# ---- packed rays: one alpha per boundary point, the last of every pack is 0 (or uses the appended cdf)
+def neus_packed_cdf_to_alpha(cdf, pack_infos, append_cdf_1=False, pack_cdf_appends=None):
+    if append_cdf_1:
+        pack_cdf_appends = cdf.new_full((pack_infos.shape[0],), 1.)
+    drop = -1 * packed_diff(cdf, pack_infos, pack_appends=pack_cdf_appends)
+    return (drop / (cdf + 1e-5)).clamp_min(0)
+
+
+def neus_packed_sdf_to_alpha(sdf, inv_s, pack_infos, append_cdf_1=False, pack_sdf_appends=None):
+    app = None if pack_sdf_appends is None else torch.sigmoid(pack_sdf_appends * inv_s)
+    return neus_packed_cdf_to_alpha(torch.sigmoid(sdf * inv_s), pack_infos, append_cdf_1, app)
+
+
+@torch.no_grad()
+def neus_packed_sdf_to_upsample_alpha(sdf, depth_samples, inv_s, pack_infos):
+    """Up-sampling alpha of the original NeuS: re-estimate the sdf at both ends of an interval from the mid value
+    and the (clamped, non-increasing) slope, then take the cdf drop (neus_utils.py:164-188)."""
+    d_sdf = packed_diff(sdf, pack_infos)
+    d_t = packed_diff(depth_samples, pack_infos)
+    mid = sdf + d_sdf * 0.5
+    slope = d_sdf / (d_t + 1e-5)
+    prev = slope.roll(1).index_fill_(0, pack_infos[:, 0], 0)
+    slope = torch.minimum(prev, slope).clamp_(-10, 0)
+    ends = torch.addcmul(mid.unsqueeze(-1).to(depth_samples.dtype), slope.unsqueeze(-1),
+                         d_t.unsqueeze(-1) * d_t.new_tensor([-0.5, 0.5]))
+    cdf = torch.sigmoid(ends * inv_s)
+    return ((cdf[..., 0] - cdf[..., 1]) / (cdf[..., 0] + 1e-5)).clamp_min_(0)
+
+
+@torch.no_grad()
+def neus_ray_sdf_to_upsample_alpha(sdf, depth_samples, inv_s):
+    d_sdf, d_t = sdf.diff(dim=-1), depth_samples.diff(dim=-1)
+    mid = (sdf[..., :-1] + sdf[..., 1:]) * 0.5
+    slope = d_sdf / (d_t + 1e-5)
+    prev = torch.cat([slope.new_zeros([*slope.shape[:-1], 1]), slope[..., :-1]], -1)
+    slope = torch.minimum(prev, slope).clamp_(-10.0, 0.0)
+    ends = torch.addcmul(mid.unsqueeze(-1), slope.unsqueeze(-1), d_t.unsqueeze(-1) * d_t.new_tensor([-0.5, 0.5]))
+    cdf = torch.sigmoid(ends * inv_s)
+    return ((cdf[..., 0] - cdf[..., 1]) / (cdf[..., 0] + 1e-5)).clamp_min_(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths, *, nablas_has_grad,
+                      with_rgb, with_normal, dtype):
+    x = torch.addcmul(rays_o[ridx_all], rays_d[ridx_all], depths.unsqueeze(-1))
+    kw = dict(x=x, nablas_has_grad=nablas_has_grad, with_rgb=with_rgb, with_normal=with_normal)
+    if rays_h_appear is not None:
+        kw["h_appear"] = rays_h_appear[ridx_all]
+    if view_dirs is not None:
+        kw["v"] = view_dirs[ridx_all]
+    out = model.forward(**kw)
+    volume_buffer["net_x"] = x
+    if "nablas" in out:
+        volume_buffer["nablas"] = out["nablas"].to(dtype)
+    if "rgb" in out:
+        volume_buffer["rgb"] = out["rgb"].to(dtype)
+
+
+def neus_ray_query_march_occ_multi_upsample_compressed(
+        model, ray_tested, with_rgb=True, with_normal=True, perturb=False, nablas_has_grad=False, forward_inv_s=None,
+        num_coarse=0, coarse_step_cfg=dict(step_mode="linear"), chunksize_query=2 ** 24, march_cfg=dict(), num_fine=8,
+        upsample_inv_s=64., upsample_s_divisor=1.0, upsample_inv_s_factors=(1, 4, 16), upsample_use_estimate_alpha=False):
+    """Occupancy-grid march -> multi-stage NeuS up-sampling -> (optional coarse samples) -> SDF with grad -> alpha ->
+    sample compression -> colour / normal query.  See the module docstring for the contract."""
+    empty = dict(type="empty", rays_inds_hit=[])
+    if ray_tested["num_rays"] == 0:
+        return empty, {}
+    use_h_appear = getattr(model, "use_h_appear", False) and with_rgb
+    use_view_dirs = getattr(model, "use_view_dirs", False) and with_rgb
+    n_stage = len(upsample_inv_s_factors)
+    if isinstance(num_fine, int):
+        num_fine = [num_fine] * n_stage
+    assert len(num_fine) == n_stage, f"num_fine should be of the same length={n_stage} with upsample"
+    num_fine = [n // 2 * 2 + 1 for n in num_fine]
+    upsample_inv_s = upsample_inv_s / upsample_s_divisor
+    forward_inv_s = model.forward_inv_s() if forward_inv_s is None else forward_inv_s
+    step_mode = coarse_step_cfg.get("step_mode", "linear")
+    if num_coarse > 0 and step_mode != "linear":
+        raise RuntimeError(f"coarse step_mode={step_mode!r} is not built (CFG uses 'linear')")
+
+    rays_o, rays_d, near, far, rays_inds = itemgetter("rays_o", "rays_d", "near", "far", "rays_inds")(ray_tested)
+    rays_h_appear = ray_tested["rays_h_appear"] if use_h_appear else None
+    device, dtype = rays_o.device, rays_o.dtype
+    R = rays_o.shape[0]
+    dir_scale = rays_d.detach().norm(dim=-1)
+    view_dirs = rays_d / dir_scale.clamp_min(1.0e-10).unsqueeze(-1) if use_view_dirs else None
+
+    if num_coarse > 0:
+        depths_coarse_1, deltas_coarse_1 = batch_sample_step_linear(near, far, num_coarse + 1, perturb=perturb, return_dt=True)
+    marched = model.accel.ray_march(rays_o, rays_d, near=near, far=far, perturb=perturb, **march_cfg)
+    net_kw = dict(nablas_has_grad=nablas_has_grad, with_rgb=with_rgb, with_normal=with_normal, dtype=dtype)
+
+    if marched.ridx_hit is not None:
+        # ---------------- up-sample on the marched samples (no grad)
+        pack_infos = marched.pack_infos.clone()
+        depth_samples = marched.depth_samples
+        n_hit = marched.num_hit_rays
+        rays_inds_hit = rays_inds[marched.ridx_hit]
+        with torch.no_grad():
+            sdf = model.forward_sdf(marched.samples)["sdf"].to(dtype)
+            fine_stages = []
+            for i, factor in enumerate(upsample_inv_s_factors):
+                if upsample_use_estimate_alpha:
+                    alpha = neus_packed_sdf_to_upsample_alpha(sdf, depth_samples, upsample_inv_s * factor, pack_infos)
+                else:
+                    alpha = neus_packed_sdf_to_alpha(sdf, upsample_inv_s * factor, pack_infos)
+                vw = packed_alpha_to_vw(alpha, pack_infos)
+                cdf = packed_cumsum(vw, pack_infos, exclusive=True)
+                norm = cdf[pack_infos[:, 0] + pack_infos[:, 1] - 1].clamp_min(1e-5)
+                cdf = packed_div(cdf, norm, pack_infos)
+                fine = packed_sample_cdf(depth_samples, cdf, pack_infos, num_fine[i], perturb=perturb)[0]
+                fine_stages.append(fine)
+                if n_stage > 1:
+                    pinfo_fine = get_pack_infos_from_batch(n_hit, num_fine[i], device=device)
+                    pidx0, pidx1, pack_infos = merge_two_packs_sorted_aligned(depth_samples, pack_infos, fine.flatten(), pinfo_fine, b_sorted=True)
+                    n_old = depth_samples.numel()
+                    merged = depth_samples.new_empty([n_old + fine.numel()])
+                    merged[pidx0], merged[pidx1] = depth_samples, fine.flatten()
+                    depth_samples = merged
+                    if i < n_stage - 1:
+                        sdf_fine = model.forward_sdf_on_rays(marched.ridx_hit, fine, rays_o, rays_d)["sdf"].to(dtype)
+                        sdf_new = sdf.new_empty([n_old + fine.numel()])
+                        sdf_new[pidx0], sdf_new[pidx1] = sdf, sdf_fine.flatten()
+                        sdf = sdf_new
+            depths_1 = torch.cat(fine_stages, dim=-1).sort(dim=-1).values if n_stage > 1 else fine_stages[0]
+
+        # ---------------- boundary points with grad, alpha, compression
+        if num_coarse == 0:
+            x = torch.addcmul(rays_o[marched.ridx_hit].unsqueeze(-2), rays_d[marched.ridx_hit].unsqueeze(-2), depths_1.unsqueeze(-1))
+            alpha = neus_ray_sdf_to_alpha(model.forward_sdf(x.flatten(0, -2))["sdf"].to(dtype).view(depths_1.shape), forward_inv_s)
+            depths = depths_1[..., :-1] + depths_1.diff(dim=-1) / 2.
+            pack_infos = get_pack_infos_from_batch(n_hit, depths.size(-1), device=device)
+            nidx_useful, pack_infos_useful, pidx_useful = packed_volume_render_compression(alpha.flatten(), pack_infos)
+            if nidx_useful.numel() == 0:
+                return empty, {}
+            depths_packed, alpha_packed = depths.flatten()[pidx_useful], alpha.flatten()[pidx_useful]
+            volume_buffer = dict(type="packed", rays_inds_hit=rays_inds_hit[nidx_useful], pack_infos_hit=pack_infos_useful,
+                                 t=depths_packed.to(dtype), opacity_alpha=alpha_packed.to(dtype))
+            if with_rgb or with_normal:
+                ridx_all = marched.ridx_hit.unsqueeze(-1).expand(n_hit, depths.size(-1)).flatten()[pidx_useful]
+                _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths_packed, **net_kw)
+            details = {"march.num_per_ray": marched.pack_infos[:, 1], "render.num_per_ray0": depths.size(-1),
+                       "render.num_per_ray": pack_infos_useful[:, 1]}
+            return volume_buffer, details
+
+        ridx_coarse = torch.arange(R, device=device)
+        pidx0, pidx1, pack_infos = merge_two_batch_a_includes_b(depths_coarse_1, ridx_coarse, depths_1, marched.ridx_hit, a_sorted=True)
+        S = depths_1.numel() + depths_coarse_1.numel()
+        depths_1_packed = depths_1.new_zeros([S])
+        ridx_all = marched.ridx_hit.new_zeros([S])
+        ridx_all[pidx0], ridx_all[pidx1] = ridx_coarse.unsqueeze(-1), marched.ridx_hit.unsqueeze(-1)
+        depths_1_packed[pidx0], depths_1_packed[pidx1] = depths_coarse_1, depths_1
+        depths_packed = depths_1_packed + packed_diff(depths_1_packed, pack_infos) / 2.
+        sdf_b = model.forward_sdf_on_rays(ridx_all, depths_1_packed, rays_o, rays_d)["sdf"].to(dtype)
+        alpha_packed = neus_packed_sdf_to_alpha(sdf_b, forward_inv_s, pack_infos)
+        nidx_useful, pack_infos_useful, pidx_useful = packed_volume_render_compression(alpha_packed, pack_infos)
+        if nidx_useful.numel() == 0:
+            return empty, {}
+        ridx_all, depths_packed, alpha_packed = ridx_all[pidx_useful], depths_packed[pidx_useful], alpha_packed[pidx_useful]
+        volume_buffer = dict(type="packed", rays_inds_hit=rays_inds[nidx_useful], pack_infos_hit=pack_infos_useful,
+                             t=depths_packed.to(dtype), opacity_alpha=alpha_packed.to(dtype))
+        if with_rgb or with_normal:
+            _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths_packed, **net_kw)
+        details = {"march.num_per_ray": marched.pack_infos[:, 1], "render.num_per_ray0": pack_infos[:, 1],
+                   "render.num_per_ray": pack_infos_useful[:, 1]}
+        return volume_buffer, details
+
+    # ---------------- no ray hit the occupancy grid
+    if num_coarse == 0:
+        return empty, {}
+    x = torch.addcmul(rays_o.unsqueeze(-2), rays_d.unsqueeze(-2), depths_coarse_1.unsqueeze(-1))
+    sdf_c = model.forward_sdf(x.flatten(0, -2))["sdf"].to(dtype).view(depths_coarse_1.shape)
+    alpha_coarse = neus_ray_sdf_to_alpha(sdf_c, forward_inv_s)
+    depths_coarse = depths_coarse_1[..., :num_coarse] + deltas_coarse_1[..., :num_coarse] / 2.
+    pack_infos_coarse = get_pack_infos_from_batch(R, num_coarse, device=device)
+    nidx_useful, pack_infos_useful, pidx_useful = packed_volume_render_compression(alpha_coarse.flatten(), pack_infos_coarse)
+    if nidx_useful.numel() == 0:
+        return empty, {}
+    depths_packed, alpha_packed = depths_coarse.flatten()[pidx_useful], alpha_coarse.flatten()[pidx_useful]
+    volume_buffer = dict(type="packed", rays_inds_hit=rays_inds[nidx_useful], pack_infos_hit=pack_infos_useful,
+                         t=depths_packed.to(dtype), opacity_alpha=alpha_packed.to(dtype))
+    if with_rgb or with_normal:
+        ridx_all = torch.arange(R, device=device).unsqueeze(-1).expand_as(depths_coarse).flatten()[pidx_useful]
+        _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths_packed, **net_kw)
+    return volume_buffer, {"render.num_per_ray0": depths_coarse.size(-1), "render.num_per_ray": pack_infos_useful[:, 1]}

@@ -1,0 +1,77 @@
+"""Single-object volume renderer -- the call path of `app.renderers.SingleVolumeRenderer` for one close-range NeuS
+model (reference: app/renderers/single_volume_renderer.py:73-102,136-460,495-620): ray_test -> model.ray_query ->
+volume integration -> rendered dict, chunked over rays for full images.
+
+The reference resolves models / cameras through its scene graph (app/resources, out of scope here); this renderer
+takes the model and the rays directly.  `render()` is what bench.py times.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .fields.neus import LoTDNeuSModel, volume_integration
+
+
+class SingleVolumeRenderer:
+    def __init__(self, config: dict = None):
+        cfg = dict(near=0.01, far=None, with_rgb=True, with_normal=True, perturb=False, rayschunk=0, depth_use_normalized_vw=True)
+        cfg.update(config or {})
+        self.config = cfg
+        self.training = True
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def _volume_integration(self, volume_buffer, rendered):
+        return volume_integration(volume_buffer, rendered, training=self.training,
+                                  depth_use_normalized_vw=self.config["depth_use_normalized_vw"], nablas_key="nablas_in_world")
+
+    def ray_query(self, model: LoTDNeuSModel, rays_o, rays_d, rays_h_appear=None, near=None, far=None, return_buffer=True,
+                  return_details=False) -> Dict:
+        """One chunk of rays: -> dict(rendered={rgb_volume, depth_volume, mask_volume, normals_volume}, volume_buffer, details)."""
+        cfg = self.config
+        near = cfg["near"] if near is None else near
+        far = cfg["far"] if far is None else far
+        n, device = rays_o.shape[0], rays_o.device
+        extra = {} if rays_h_appear is None else dict(rays_h_appear=rays_h_appear)
+        ray_tested = model.ray_test(rays_o, rays_d, near=near, far=far, **extra)
+        rendered = dict(depth_volume=torch.zeros(n, device=device), mask_volume=torch.zeros(n, device=device))
+        if cfg["with_rgb"]:
+            rendered["rgb_volume"] = torch.zeros(n, 3, device=device)
+        if cfg["with_normal"]:
+            rendered["normals_volume"] = torch.zeros(n, 3, device=device)
+        ret = dict(rendered=rendered, ray_tested=ray_tested)
+        qcfg = dict(model.ray_query_cfg)
+        qcfg.update(with_rgb=cfg["with_rgb"], with_normal=cfg["with_normal"], perturb=cfg["perturb"])
+        raw = model.ray_query(ray_tested=ray_tested, config=qcfg, return_buffer=True, return_details=return_details)
+        vb = raw["volume_buffer"]
+        if vb["type"] != "empty":
+            if "nablas" in vb:
+                # obj -> world rotation is the identity for a single static object (single_volume_renderer.py:262-276)
+                vb["nablas_in_world"] = vb["nablas"]
+            self._volume_integration(vb, rendered)
+        if return_buffer:
+            ret["volume_buffer"] = vb
+        if return_details:
+            ret["details"] = raw.get("details", {})
+        return ret
+
+    def render(self, model: LoTDNeuSModel, rays_o, rays_d, rays_h_appear=None, near=None, far=None, rayschunk=None,
+               return_buffer=False, return_details=False) -> Dict:
+        """Whole batch / image; with `rayschunk` > 0 the rays are processed in chunks (batchify_query, models/utils.py:441)."""
+        chunk = self.config["rayschunk"] if rayschunk is None else rayschunk
+        n = rays_o.shape[0]
+        if not chunk or chunk >= n:
+            return self.ray_query(model, rays_o, rays_d, rays_h_appear, near, far, return_buffer, return_details)
+        outs = []
+        for s in range(0, n, chunk):
+            e = min(s + chunk, n)
+            ha = None if rays_h_appear is None else rays_h_appear[s:e]
+            outs.append(self.ray_query(model, rays_o[s:e], rays_d[s:e], ha, near, far, False, False)["rendered"])
+        return dict(rendered={k: torch.cat([o[k] for o in outs], 0) for k in outs[0]})

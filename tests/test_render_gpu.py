@@ -1,0 +1,95 @@
+"""End-to-end parity of the rendering path: neuralsim_b200 (CUDA) vs the CPU oracle on identical rays, weights and grid.
+Tolerance from BASELINE.json north_star: rendered RGB / depth / normals within 1e-4 relative L2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import render as orender
+from oracle import scene as oscene
+from util import make_pair, product_grads, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-4
+
+
+def _rays(H=30, W=40, k=1):
+    return oscene.pinhole_rays(H, W, oscene.orbit_camera(k, 8, radius=3.0, elev_deg=25.0))
+
+
+def _oracle_render(P, ro, rd, training=True, perturb=False):
+    rt = orender.ray_test(ro, rd, near=0.01)
+    vb, det = orender.neus_ray_query(P, oscene.make_occ_grid(), rt, rays_h_appear=torch.zeros(rt["num_rays"], P.n_appear), perturb=perturb)
+    return orender.volume_integration(vb, ro.shape[0], training=training), vb, det, rt
+
+
+def _product_render(model, ro, rd, cuda, training=True):
+    from neuralsim_b200.renderer import SingleVolumeRenderer
+    r = SingleVolumeRenderer(dict(near=0.01)).train(training)
+    model.train(training)
+    return r.render(model, ro.to(cuda), rd.to(cuda), rays_h_appear=torch.zeros(ro.shape[0], 4, device=cuda), return_buffer=True, return_details=True)
+
+
+@pytest.mark.parametrize("ln_inv_s", [0.2996, 0.5298, 0.7601])      # inv_s = 20, 200, 2000
+def test_forward_parity(cuda, ln_inv_s):
+    P, model = make_pair(cuda, ln_inv_s_init=ln_inv_s)
+    ro, rd = _rays()
+    with torch.no_grad():
+        ref, vb_ref, det_ref, rt = _oracle_render(P, ro, rd)
+        out = _product_render(model, ro, rd, cuda)
+    got, vb = out["rendered"], out["volume_buffer"]
+    # integer structure: hit rays, marched sample counts
+    assert torch.equal(out["ray_tested"]["rays_inds"].cpu(), rt["rays_inds"])
+    assert torch.equal(out["details"]["march.num_per_ray"].cpu(), det_ref["march.num_per_ray"])
+    for k in ("rgb_volume", "depth_volume", "normals_volume", "mask_volume"):
+        assert rel_l2(got[k], ref[k]) <= TOL, (k, rel_l2(got[k], ref[k]))
+    assert float(got["mask_volume"].sum()) > 50.0                      # the sphere is actually rendered
+
+
+def test_backward_parity(cuda):
+    P, model = make_pair(cuda)
+    ro, rd = _rays(24, 32, 3)
+    P.requires_grad_(True)
+    ref, *_ = _oracle_render(P, ro, rd)
+    loss_ref = sum(v.mean() for v in ref.values())
+    loss_ref.backward()
+    out = _product_render(model, ro, rd, cuda)["rendered"]
+    loss = sum(v.mean() for v in out.values())
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    g = product_grads(model)
+    for k, t in P.tensors().items():
+        assert g[k] is not None, k
+        # fp16 rounding of cotangents in the autocast graph is replayed by both sides; what remains is
+        # accumulation order (and cuBLAS vs CPU GEMM) -> loose relative tolerance
+        assert rel_l2(g[k], t.grad) <= 2e-2, (k, rel_l2(g[k], t.grad))
+
+
+def test_eval_mode_and_chunking(cuda):
+    P, model = make_pair(cuda)
+    ro, rd = _rays(20, 28, 5)
+    from neuralsim_b200.renderer import SingleVolumeRenderer
+    r = SingleVolumeRenderer(dict(near=0.01)).eval()
+    model.eval()
+    with torch.no_grad():
+        ref, *_ = _oracle_render(P, ro, rd, training=False)
+        a = r.render(model, ro.to(cuda), rd.to(cuda), rays_h_appear=torch.zeros(ro.shape[0], 4, device=cuda))["rendered"]
+        b = r.render(model, ro.to(cuda), rd.to(cuda), rays_h_appear=torch.zeros(ro.shape[0], 4, device=cuda), rayschunk=137)["rendered"]
+    for k in a:
+        assert rel_l2(a[k], ref[k]) <= TOL, k
+        assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), k       # rays are independent: chunking changes nothing
+
+
+def test_no_hit_and_empty_inputs(cuda):
+    P, model = make_pair(cuda)
+    from neuralsim_b200.renderer import SingleVolumeRenderer
+    r = SingleVolumeRenderer(dict(near=0.01))
+    o = torch.tensor([[5., 5, 5], [0., 0, -3]], device=cuda); d = torch.tensor([[0., 0, 1], [0.9, 0.1, 0.3]], device=cuda)
+    d = torch.nn.functional.normalize(d, dim=-1)
+    out = r.render(model, o, d, rays_h_appear=torch.zeros(2, 4, device=cuda))["rendered"]          # rays that miss the box
+    assert float(out["mask_volume"].abs().sum()) == 0.0
+    model.accel.occ.set_occ_grid(torch.zeros(64, 64, 64, dtype=torch.bool))                         # nothing occupied: coarse-only branch
+    ro, rd = _rays(8, 8, 0)
+    out = r.render(model, ro.to(cuda), rd.to(cuda), rays_h_appear=torch.zeros(64, 4, device=cuda))["rendered"]
+    assert torch.isfinite(out["rgb_volume"]).all()
+    out = r.render(model, ro[:0].to(cuda), rd[:0].to(cuda), rays_h_appear=torch.zeros(0, 4, device=cuda))["rendered"]
+    assert out["rgb_volume"].shape == (0, 3)
