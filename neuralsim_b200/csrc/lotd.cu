@@ -281,9 +281,8 @@ int dispatch_DF(const nsb_lotd_meta *meta, const char *who, Fn &&fn) {
 
 extern "C" int nsb_lotd_fwd(const nsb_lotd_meta *meta, const float *input, const void *params, int params_is_half,
                             int64_t n, int32_t max_level, void *y, float *dy_dx, void *stream) {
-    NSB_REQUIRE(meta && y, "nsb_lotd_fwd: NULL argument");
     if (n == 0) return 0;
-    NSB_REQUIRE(input && params, "nsb_lotd_fwd: NULL argument");
+    NSB_REQUIRE(meta && y && input && params, "nsb_lotd_fwd: NULL argument");
     PLMeta m;
     if (make_plmeta(meta, &m)) return 2;
     cudaStream_t s = (cudaStream_t)stream;

@@ -403,7 +403,7 @@ def merge_two_batch_a_includes_b(vals_a, nidx_a, vals_b, nidx_b, a_sorted=True, 
     n_per[where_b] = wa + wb
     pack_infos = get_pack_infos_from_n(n_per)
     first = pack_infos[:, 0:1]
-    rank = torch.cat([vals_a[where_b], vals_b], 1).detach().argsort(-1, stable=True).argsort(-1)
+    rank = torch.cat([vals_a[where_b], vals_b], 1).detach().argsort(dim=-1, stable=True).argsort(dim=-1)
     if a_sorted:
         pidx_a = first + torch.arange(wa, device=device)[None, :]
     else:

@@ -34,7 +34,7 @@ def test_fused_sdf_vs_oracle_and_autocast(cuda):
     assert frac < 2e-2 and worst <= 2.0, (frac, worst)
     frac, worst = _ulp16_mismatch(sdf_fused.cpu(), sdf_oracle)
     assert frac < 2e-2 and worst <= 2.0, (frac, worst)
-    assert float((sdf_fused.cpu() - (x.norm(dim=-1) - 0.5)).abs().max()) < 0.02   # the synthetic scene is a sphere
+    assert float((sdf_fused.cpu() - (x.norm(dim=-1) - 0.5)).abs().max()) < 0.05   # the synthetic scene is a sphere
 
 
 def test_fused_sdf_rays_matches_points(cuda):

@@ -43,7 +43,7 @@ def test_single_grid_bit_exact(cuda, grid_kind, dt_gamma):
     assert torch.equal(got[1].squeeze(-1).cpu(), ref[1]) and torch.equal(got[2].squeeze(-1).cpu(), ref[2])  # t bit-exact
     if grid_kind == "empty":
         assert got[1].shape[0] == 0
-    if grid_kind == "full":
+    if grid_kind == "full" and dt_gamma == 0.0:
         assert int(got[0][:, 1].max()) == 256                                  # max_steps cap
 
 

@@ -121,7 +121,9 @@ def test_alpha_to_vw_and_compression(cuda, data):
         gw = torch.from_numpy(rng.normal(size=S).astype(np.float32))
         ga_ref = opk.packed_alpha_to_vw_backward(w_ref, gw, a, pi, 1e-4, thre)
         ga = B.packed_alpha_to_vw_backward(w, gw.to(cuda), a.to(cuda), pi.to(cuda), 1e-4, thre)
-        assert torch.allclose(ga.cpu(), ga_ref, rtol=1e-4, atol=1e-5)
+        # cotangents are divided by (1 - alpha) ~ 1e-3 for the near-opaque samples: compare relative to the pack scale
+        assert float((ga.cpu() - ga_ref).norm() / ga_ref.norm()) < 1e-4
+        assert torch.allclose(ga.cpu(), ga_ref, rtol=1e-3, atol=1e-3 * float(ga_ref.abs().max()))
 
 
 def test_producers_sort_boundaries(cuda, data):
