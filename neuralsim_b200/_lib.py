@@ -94,3 +94,55 @@ def c_i32(v):
 
 def c_f32(v):
     return ctypes.c_float(float(v))
+
+
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of this library's kernels (bench.py's roofline numbers).  Disabled by
+    default: then `time()` costs one attribute test.  Events are recorded on the current stream, i.e. the stream the
+    kernels are launched on."""
+
+    def __init__(self):
+        self.enabled = False
+        self._rec = {}
+
+    def enable(self):
+        self._rec, self.enabled = {}, True
+
+    def disable(self):
+        self.enabled = False
+
+    class _Span:
+        def __init__(self, owner, name, units):
+            self.o, self.name, self.units = owner, name, units
+
+        def __enter__(self):
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+        def __exit__(self, *exc):
+            self.b.record()
+            self.o._rec.setdefault(self.name, []).append((self.a, self.b, self.units))
+
+    class _Null:
+        def __enter__(self):
+            return None
+
+        def __exit__(self, *exc):
+            return False
+
+    _NULL = _Null()
+
+    def time(self, name, units=0):
+        return self._Span(self, name, units) if self.enabled else self._NULL
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, spans in self._rec.items():
+            out[name] = dict(ms=float(sum(a.elapsed_time(b) for a, b, _ in spans)), units=int(sum(u for _, _, u in spans)),
+                             launches=len(spans))
+        return out
+
+
+KERNEL_TIMER = KernelTimer()

@@ -108,9 +108,10 @@ def lod_fwd(lod_meta, input, params, batch_inds=None, batch_offsets=None, batch_
     y = torch.empty((n, lod_meta.n_encoded_dims), dtype=params.dtype, device=input.device)
     dy_dx = torch.empty((n, lod_meta.n_encoded_dims * lod_meta.n_dims_to_encode), dtype=torch.float32,
                         device=input.device) if need else None
-    L.check(L.lib().nsb_lotd_fwd(lod_meta.c_ref, L.ptr(input, "f32", "input"), L.ptr(params, None, "params"),
-                                 ctypes.c_int(params.dtype == torch.float16), L.c_i64(n), L.c_i32(ml), L.ptr(y),
-                                 L.ptr(dy_dx, "f32", allow_none=True), L.stream_ptr()), "lod_fwd")
+    with L.KERNEL_TIMER.time("lotd_gather", n):
+        L.check(L.lib().nsb_lotd_fwd(lod_meta.c_ref, L.ptr(input, "f32", "input"), L.ptr(params, None, "params"),
+                                     ctypes.c_int(params.dtype == torch.float16), L.c_i64(n), L.c_i32(ml), L.ptr(y),
+                                     L.ptr(dy_dx, "f32", allow_none=True), L.stream_ptr()), "lod_fwd")
     return y, dy_dx
 
 
@@ -137,8 +138,9 @@ def lod_bwd(lod_meta, dL_dy, input, params, dy_dx=None, batch_inds=None, batch_o
                                            L.c_f32(1.0), L.ptr(dL_dx), L.stream_ptr()), "lod_bwd")
     if need_p:
         acc = torch.zeros(params.shape[0], dtype=torch.float32, device=input.device)
-        L.check(L.lib().nsb_lotd_bwd_grid(lod_meta.c_ref, L.ptr(dL_dy), is_half, L.ptr(input, "f32", "input"), L.c_i64(n),
-                                          L.c_i32(ml), L.c_f32(1.0), L.ptr(acc), L.stream_ptr()), "lod_bwd")
+        with L.KERNEL_TIMER.time("lotd_bwd_grid", n):
+            L.check(L.lib().nsb_lotd_bwd_grid(lod_meta.c_ref, L.ptr(dL_dy), is_half, L.ptr(input, "f32", "input"), L.c_i64(n),
+                                              L.c_i32(ml), L.c_f32(1.0), L.ptr(acc), L.stream_ptr()), "lod_bwd")
         dL_dp = acc.to(params.dtype)
     return dL_dx, dL_dp
 
@@ -160,7 +162,8 @@ def lod_bwd_bwd_input(lod_meta, dL_ddLdx, dL_dy, input, params, dy_dx=None, batc
     acc = torch.zeros(params.shape[0], dtype=torch.float32, device=input.device) if need_p else None
     if need_y and dy_dx is None:
         raise RuntimeError("LoTDEncoding::bwd_bwd_input: need `dy_dx` to compute `dL_d(dLdy)`.")
-    L.check(L.lib().nsb_lotd_bwd_bwd_input(
+    with L.KERNEL_TIMER.time("lotd_bwd_bwd", n):
+      L.check(L.lib().nsb_lotd_bwd_bwd_input(
         lod_meta.c_ref, L.ptr(dL_ddLdx.contiguous(), "f32", "dL_ddLdx"), L.ptr(dL_dy), ctypes.c_int(dL_dy.dtype == torch.float16),
         L.ptr(input, "f32", "input"), L.ptr(None if dy_dx is None else dy_dx.contiguous(), "f32", allow_none=True),
         L.c_i64(n), L.c_i32(ml), L.c_f32(1.0), L.ptr(out_y, allow_none=True), L.ptr(acc, allow_none=True),

@@ -31,7 +31,8 @@ def _march(rays_o, rays_d, t_min, t_max, roi, grid_binary, batch_inds, type, ste
             L.c_i32(res[0]), L.c_i32(res[1]), L.c_i32(res[2]), L.ptr(g, "u8"), L.c_f32(step_size), L.c_f32(max_step_size),
             L.c_f32(dt_gamma), ctypes.c_uint32(int(max_steps)))
     num_steps = torch.empty(R, dtype=torch.int32, device=dev)
-    L.check(L.lib().nsb_ray_marching(*args, None, L.ptr(num_steps), None, None, None, None, None, L.stream_ptr()), who)
+    with L.KERNEL_TIMER.time("march", R):
+        L.check(L.lib().nsb_ray_marching(*args, None, L.ptr(num_steps), None, None, None, None, None, L.stream_ptr()), who)
     cum = num_steps.cumsum(0, dtype=torch.int32)
     packed_info = torch.stack([cum - num_steps, num_steps], 1).contiguous()
     total = int(cum[-1].item()) if R > 0 else 0          # output size is data dependent: one sync, as the reference
@@ -41,8 +42,9 @@ def _march(rays_o, rays_d, t_min, t_max, roi, grid_binary, batch_inds, type, ste
     gidx = torch.empty(total, dtype=torch.int32, device=dev) if return_gidx else None
     bidx = torch.empty(total, dtype=torch.int32, device=dev) if batch_inds is not None else None
     if total > 0:
-        L.check(L.lib().nsb_ray_marching(*args, L.ptr(packed_info), None, L.ptr(t_starts), L.ptr(t_ends), L.ptr(ridx),
-                                         L.ptr(gidx, allow_none=True), L.ptr(bidx, allow_none=True), L.stream_ptr()), who)
+        with L.KERNEL_TIMER.time("march", R):
+            L.check(L.lib().nsb_ray_marching(*args, L.ptr(packed_info), None, L.ptr(t_starts), L.ptr(t_ends), L.ptr(ridx),
+                                             L.ptr(gidx, allow_none=True), L.ptr(bidx, allow_none=True), L.stream_ptr()), who)
     return packed_info, t_starts, t_ends, ridx, gidx, bidx
 
 

@@ -204,7 +204,8 @@ class LoTDSDF(nn.Module):
         xf = x.reshape(-1, 3).contiguous().float()
         sdf = torch.empty(xf.shape[0], dtype=torch.float32, device=xf.device)
         ml = self.encoding.meta.n_levels if (max_level or self.encoding.max_level) is None else int(max_level or self.encoding.max_level)
-        L.check(L.lib().nsb_fused_sdf(self.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(xf, "f32"),
+        with L.KERNEL_TIMER.time("lotd_gather", xf.shape[0]):
+          L.check(L.lib().nsb_fused_sdf(self.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(xf, "f32"),
                                       L.c_i64(xf.shape[0]), L.c_i32(ml), L.ptr(sdf), None, L.stream_ptr()), "fused_sdf")
         return sdf.view(prefix)
 
@@ -217,7 +218,8 @@ class LoTDSDF(nn.Module):
         ridx, tf = ridx.reshape(-1).contiguous().long(), t.reshape(-1).contiguous().float()
         sdf = torch.empty(tf.shape[0], dtype=torch.float32, device=tf.device)
         ml = self.encoding.meta.n_levels if (max_level or self.encoding.max_level) is None else int(max_level or self.encoding.max_level)
-        L.check(L.lib().nsb_fused_sdf_rays(self.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o.contiguous(), "f32"),
+        with L.KERNEL_TIMER.time("lotd_gather", tf.shape[0]):
+          L.check(L.lib().nsb_fused_sdf_rays(self.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o.contiguous(), "f32"),
                                            L.ptr(rays_d.contiguous(), "f32"), L.ptr(ridx, "i64"), L.ptr(tf, "f32"), L.c_i64(tf.shape[0]),
                                            L.c_i32(ml), L.ptr(sdf), L.stream_ptr()), "fused_sdf_rays")
         return sdf.view(shape)
