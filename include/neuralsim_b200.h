@@ -53,6 +53,8 @@ const char *nsb_last_error(void);
 int nsb_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
 uint64_t nsb_launch_count(void);
+/* Self-check switches: key "sdf_simt" (0|1) routes nsb_fused_sdf* through the CUDA-core cross-check kernel. */
+int nsb_set_option(const char *key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * _lotd  (csrc/lotd/src/lotd.cpp:22-107)
@@ -172,6 +174,15 @@ int nsb_fused_sdf(const nsb_lotd_meta *meta_host, const void *params_half, const
 int nsb_fused_sdf_rays(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host,
                        const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
                        int32_t max_level, float *sdf, void *stream);
+
+/* Backward of nsb_fused_sdf / nsb_fused_sdf_rays wrt. the table and the decoder weights (nothing is saved by the
+ * forward: features and pre-activations are recomputed).  Pass x != NULL, or x == NULL with (rays_o, rays_d, ridx, t).
+ * All outputs are fp32 and ACCUMULATED into (caller zero-fills): d_grid[P], d_W1[W*F], d_b1[W], d_W2[W], d_b2[1].
+ * Replaces the autograd chain LoTDFunction.backward (lotd.py:83-119) + the autocast MLP backward. */
+int nsb_fused_sdf_bwd(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host,
+                      const float *x, const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t,
+                      const float *d_sdf, int64_t n, int32_t max_level, float *d_grid, float *d_W1, float *d_b1,
+                      float *d_W2, float *d_b2, void *stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,16 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace nsb
 
+namespace nsb { std::atomic<int> g_opt_sdf_simt{0}; }
+
+// Tunables / self-check switches.  "sdf_simt" = 1 routes nsb_fused_sdf* through the CUDA-core reference kernel of
+// csrc/fused.cu instead of the tcgen05 kernel (used by the tests to cross-check the two).
+extern "C" int nsb_set_option(const char *key, int value) {
+    if (key && !strcmp(key, "sdf_simt")) { nsb::g_opt_sdf_simt.store(value); return 0; }
+    nsb::set_error("nsb_set_option: unknown key '%s'", key ? key : "(null)");
+    return 2;
+}
+
 extern "C" const char *nsb_last_error(void) { return nsb::g_err; }
 extern "C" int nsb_version(void) { return 100; }
 extern "C" uint64_t nsb_launch_count(void) { return nsb::g_launches.load(); }

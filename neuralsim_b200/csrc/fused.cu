@@ -124,6 +124,10 @@ k_fused_sdf(const PLMeta m, const __half *__restrict__ grid, const DecoderDev de
 }  // namespace nsb
 
 using namespace nsb;
+namespace nsb { extern std::atomic<int> g_opt_sdf_simt; }
+extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *params_half, const nsb_sdf_decoder *dec, const float *x,
+                                       const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
+                                       int32_t max_level, float *sdf, void *stream, int from_rays);
 
 static int launch_fused_sdf(const nsb_lotd_meta *meta, const void *params_half, const nsb_sdf_decoder *dec, const float *x,
                             const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
@@ -135,6 +139,8 @@ static int launch_fused_sdf(const nsb_lotd_meta *meta, const void *params_half, 
                 "nsb_fused_sdf: built for 3-D LoTD with 16 x 2 features (got D=%u F=%u NF=%u)", meta->n_dims_to_encode,
                 meta->n_feat_per_pseudo_lvl, meta->n_encoded_dims);
     NSB_REQUIRE(dec->width >= 1 && dec->width <= kMaxW, "nsb_fused_sdf: decoder width %d out of range (<= %d)", dec->width, kMaxW);
+    if (!g_opt_sdf_simt.load() && h_out == nullptr && meta->n_pseudo_levels == 16)   // tensor-core kernel (csrc/fused_tc.cu)
+        return nsb_fused_sdf_tc_launch(meta, params_half, dec, x, rays_o, rays_d, ridx, t, n, max_level, sdf, stream, from_rays ? 1 : 0);
     PLMeta m;
     if (make_plmeta(meta, &m)) return 2;
     DecoderDev d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2,

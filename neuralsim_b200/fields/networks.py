@@ -134,6 +134,55 @@ class SHEncoder(nn.Module):
         return _sh_encoder.apply(flat, self.degree, flat.requires_grad).unflatten(0, prefix)
 
 
+class _FusedSDF(autograd.Function):
+    """sdf = decoder(LoTD(x)) as ONE op with a hand-written backward (csrc/fused_tc.cu): forward keeps nothing but its
+    inputs, backward recomputes features / pre-activations and accumulates straight into fp32 gradients of the table and
+    the four decoder tensors.  `x` is either points [N,3] or a (ridx, t, rays_o, rays_d) tuple (x = o[ridx] + d[ridx] t)."""
+
+    @staticmethod
+    def forward(ctx, owner, pts, max_level, grid, W1, b1, W2, b2):
+        grid16, dec = owner._fused_state()
+        meta = owner.encoding.meta
+        if isinstance(pts, tuple):
+            ridx, t, rays_o, rays_d = pts
+            n = t.numel()
+            sdf = torch.empty(n, dtype=torch.float32, device=t.device)
+            with L.KERNEL_TIMER.time("fused_sdf_fwd", n):
+                L.check(L.lib().nsb_fused_sdf_rays(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
+                                                   L.ptr(ridx, "i64"), L.ptr(t, "f32"), L.c_i64(n), L.c_i32(max_level), L.ptr(sdf), L.stream_ptr()), "fused_sdf")
+        else:
+            n = pts.shape[0]
+            sdf = torch.empty(n, dtype=torch.float32, device=pts.device)
+            with L.KERNEL_TIMER.time("fused_sdf_fwd", n):
+                L.check(L.lib().nsb_fused_sdf(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(pts, "f32"), L.c_i64(n), L.c_i32(max_level),
+                                              L.ptr(sdf), None, L.stream_ptr()), "fused_sdf")
+        ctx.owner, ctx.pts, ctx.max_level, ctx.n = owner, pts, max_level, n
+        ctx.held = (grid16, dec)          # the fp16 images the forward used
+        ctx.shapes = (grid.shape, W1.shape, b1.shape, W2.shape, b2.shape)
+        return sdf
+
+    @staticmethod
+    @autograd.function.once_differentiable
+    def backward(ctx, d_sdf):
+        grid16, dec = ctx.held
+        meta, dev = ctx.owner.encoding.meta, d_sdf.device
+        gs, w1s, b1s, w2s, b2s = ctx.shapes
+        d_grid = torch.zeros(gs, dtype=torch.float32, device=dev)
+        d_W1, d_b1 = torch.zeros(w1s, dtype=torch.float32, device=dev), torch.zeros(b1s, dtype=torch.float32, device=dev)
+        d_W2, d_b2 = torch.zeros(w2s, dtype=torch.float32, device=dev), torch.zeros(b2s, dtype=torch.float32, device=dev)
+        d_sdf = d_sdf.contiguous().float()
+        if isinstance(ctx.pts, tuple):
+            ridx, t, rays_o, rays_d = ctx.pts
+            args = (None, L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"), L.ptr(ridx, "i64"), L.ptr(t, "f32"))
+        else:
+            args = (L.ptr(ctx.pts, "f32"), None, None, None, None)
+        with L.KERNEL_TIMER.time("fused_sdf_bwd", ctx.n):
+            L.check(L.lib().nsb_fused_sdf_bwd(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), *args, L.ptr(d_sdf, "f32"), L.c_i64(ctx.n),
+                                              L.c_i32(ctx.max_level), L.ptr(d_grid), L.ptr(d_W1), L.ptr(d_b1), L.ptr(d_W2), L.ptr(d_b2),
+                                              L.stream_ptr()), "fused_sdf_bwd")
+        return None, None, None, d_grid, d_W1, d_b1, d_W2, d_b2
+
+
 class LoTDSDF(nn.Module):
     """LoTD encoding + MLP decoder -> sdf (and nablas by analytic back-propagation through decoder and table)."""
 
@@ -158,9 +207,34 @@ class LoTDSDF(nn.Module):
         return dict(sdf=sdf, h=h) if return_h else dict(sdf=sdf)
 
     def forward_sdf(self, x, *, max_level: int = None):
-        if not torch.is_grad_enabled() and self._fusable():
-            return dict(sdf=self.fused_sdf(x, max_level=max_level))
+        if self._fusable():
+            if not torch.is_grad_enabled():
+                return dict(sdf=self.fused_sdf(x, max_level=max_level))
+            if not x.requires_grad:
+                return dict(sdf=self.fused_sdf_autograd(x, max_level=max_level))
         return self.forward(x, return_h=False, max_level=max_level)
+
+    def _ml(self, max_level):
+        ml = max_level or self.encoding.max_level
+        return self.encoding.meta.n_levels if ml is None else int(ml)
+
+    def fused_sdf_autograd(self, x, max_level: int = None):
+        """differentiable (wrt. table + decoder) fused query on points [...,3]"""
+        d = self.decoder.layers
+        prefix = x.shape[:-1]
+        sdf = _FusedSDF.apply(self, x.detach().reshape(-1, 3).contiguous().float(), self._ml(max_level), self.encoding.flattened_params,
+                              d[0].weight, d[0].bias, d[1].weight, d[1].bias)
+        return sdf.view(prefix)
+
+    def fused_sdf_rays_autograd(self, ridx, t, rays_o, rays_d, max_level: int = None):
+        d = self.decoder.layers
+        shape = t.shape
+        if t.dim() == 2:
+            ridx = ridx.unsqueeze(-1).expand(shape)
+        pts = (ridx.reshape(-1).contiguous().long(), t.detach().reshape(-1).contiguous().float(), rays_o.detach().contiguous(),
+               rays_d.detach().contiguous())
+        sdf = _FusedSDF.apply(self, pts, self._ml(max_level), self.encoding.flattened_params, d[0].weight, d[0].bias, d[1].weight, d[1].bias)
+        return sdf.view(shape)
 
     def forward_sdf_nablas(self, x, *, has_grad: bool = None, nablas_has_grad: bool = None, max_level: int = None, grad_guard=None):
         has_grad = torch.is_grad_enabled() if has_grad is None else has_grad

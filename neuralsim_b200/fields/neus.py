@@ -63,8 +63,11 @@ class LoTDNeuS(nn.Module):
 
     def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d):
         """sdf at o[ridx] + d[ridx]*t.  No-grad calls never materialise the points (fused kernel)."""
-        if not torch.is_grad_enabled() and self.implicit_surface._fusable():
-            return dict(sdf=self.implicit_surface.fused_sdf_rays(ridx, t, rays_o, rays_d, max_level=self.max_level))
+        if self.implicit_surface._fusable():
+            if not torch.is_grad_enabled():
+                return dict(sdf=self.implicit_surface.fused_sdf_rays(ridx, t, rays_o, rays_d, max_level=self.max_level))
+            if not (t.requires_grad or rays_o.requires_grad or rays_d.requires_grad):
+                return dict(sdf=self.implicit_surface.fused_sdf_rays_autograd(ridx, t, rays_o, rays_d, max_level=self.max_level))
         if t.dim() == 2:
             x = torch.addcmul(rays_o[ridx].unsqueeze(-2), rays_d[ridx].unsqueeze(-2), t.unsqueeze(-1)).flatten(0, -2)
             return dict(sdf=self.forward_sdf(x)["sdf"].view(t.shape))

@@ -49,3 +49,51 @@ def test_fused_sdf_rays_matches_points(cuda):
         c = model.implicit_surface.fused_sdf_rays(torch.arange(500, device=cuda), t2, o, d)
         e = model.implicit_surface.fused_sdf(torch.addcmul(o.unsqueeze(1), d.unsqueeze(1), t2.unsqueeze(-1)))
     assert torch.equal(a, b) and torch.equal(c, e)
+
+
+def test_tensor_core_kernel_matches_cuda_core_kernel(cuda):
+    """csrc/fused_tc.cu (tcgen05 + TMEM) against csrc/fused.cu (CUDA cores): same rounding points, fp32 accumulation order differs."""
+    from neuralsim_b200 import _lib
+    P, model = make_pair(cuda)
+    g = torch.Generator().manual_seed(11)
+    for n in (1, 127, 128, 129, 5000, 200001):
+        x = (torch.rand(n, 3, generator=g) * 2 - 1).to(cuda)
+        with torch.no_grad():
+            _lib.check(_lib.lib().nsb_set_option(b"sdf_simt", 1))
+            ref = model.implicit_surface.fused_sdf(x)
+            _lib.check(_lib.lib().nsb_set_option(b"sdf_simt", 0))
+            got = model.implicit_surface.fused_sdf(x)
+        frac, worst = _ulp16_mismatch(got, ref)
+        assert frac < 2e-2 and worst <= 2.0, (n, frac, worst)
+
+
+def test_fused_backward_matches_autograd_chain(cuda):
+    """nsb_fused_sdf_bwd (one tcgen05 kernel) against the unfused chain LoTDFunction + autocast MLP differentiated by torch."""
+    P, model = make_pair(cuda)
+    surf = model.implicit_surface
+    g = torch.Generator().manual_seed(12)
+    for n in (77, 128, 4000, 150001):
+        x = (torch.rand(n, 3, generator=g) * 2 - 1).to(cuda)
+        w = torch.randn(n, generator=g).to(cuda)
+        params = [surf.encoding.flattened_params, *surf.decoder.parameters()]
+        sdf_a = surf.forward(x)["sdf"].float()                          # reference chain
+        ga = torch.autograd.grad((sdf_a * w).sum(), params)
+        sdf_b = surf.fused_sdf_autograd(x)
+        gb = torch.autograd.grad((sdf_b * w).sum(), params)
+        frac, worst = _ulp16_mismatch(sdf_b, sdf_a)
+        assert frac < 2e-2 and worst <= 2.0
+        names = ["grid", "W1", "b1", "W2", "b2"]
+        for k, a, b in zip(names, ga, gb):
+            err = float((a.float() - b.float()).norm() / a.float().norm().clamp_min(1e-20))
+            # the autocast chain rounds every cotangent to fp16 (and the table gradient twice); ours keeps fp32 except dz
+            assert err < 1e-2, (n, k, err)
+        # rays variant == points variant
+        o = (torch.rand(50, 3, generator=g) * 2 - 1).to(cuda); d = torch.nn.functional.normalize(torch.randn(50, 3, generator=g), dim=-1).to(cuda)
+        ridx = torch.randint(0, 50, (n,), generator=g).to(cuda); t = (torch.rand(n, generator=g) * 0.3).to(cuda)
+        s1 = surf.fused_sdf_rays_autograd(ridx, t, o, d)
+        g1 = torch.autograd.grad((s1 * w).sum(), params)
+        s2 = surf.fused_sdf_autograd(torch.addcmul(o[ridx], d[ridx], t.unsqueeze(-1)))
+        g2 = torch.autograd.grad((s2 * w).sum(), params)
+        assert torch.equal(s1, s2)
+        for a, b in zip(g1, g2):
+            assert float((a - b).norm() / a.norm().clamp_min(1e-20)) < 1e-4     # atomics: order only
