@@ -304,11 +304,15 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     kt = _lib.KERNEL_TIMER.summary()
-    gather = kt.get("lotd_gather")
+    # the hash gather lives in three kernels: k_fused_sdf_tc (no-grad and autograd forward) and k_lotd_fwd (colour points)
+    gather = None
+    for key in ("fused_sdf_fwd", "lotd_gather"):
+        if key in kt:
+            gather = kt[key] if gather is None else {k: gather[k] + kt[key][k] for k in gather}
     roof = None
     if gather:
         achieved = gather["units"] * 512.0 / (gather["ms"] * 1e-3) / 1e9     # 512 B of table per encoded point
-        roof = {"kernel": "LoTD hash gather (k_lotd_fwd / k_fused_sdf)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        roof = {"kernel": "LoTD hash gather: k_fused_sdf_tc (gather + tcgen05 decoder) and k_lotd_fwd", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "points_per_launch": gather["units"] / max(gather["launches"], 1), "launches": gather["launches"],
                 "avg_launch_ms": gather["ms"] / max(gather["launches"], 1), "share_of_step": gather["ms"] / (ms_res * args.steps),

@@ -18,6 +18,7 @@ struct PLMeta {
     uint32_t base[kMaxPseudo];      // element offset of (level, pseudo slot) inside the flat table
     uint32_t nfeat[kMaxPseudo];     // feature width of the actual level (row stride of a cell)
     uint32_t size[kMaxPseudo];      // cells of the level (hash modulus)
+    uint32_t mask[kMaxPseudo];      // size-1 when the hash modulus is a power of two, else 0
     uint32_t is_hash;               // bit p set -> hashed level
 };
 
@@ -38,6 +39,7 @@ inline int make_plmeta(const nsb_lotd_meta *m, PLMeta *o) {
         o->base[p] = m->level_offsets[l] + m->map_cnt[p] * m->n_feat_per_pseudo_lvl;
         o->nfeat[p] = m->level_n_feats[l];
         o->size[p] = m->level_sizes[l];
+        o->mask[p] = (o->size[p] & (o->size[p] - 1)) == 0 ? o->size[p] - 1 : 0;
         if (m->level_types[l] == NSB_LOD_HASH) {
             if (p >= 32) { set_error("LoTD: hashed pseudo level index >= 32 unsupported"); return 2; }
             o->is_hash |= (1u << p);
@@ -118,6 +120,56 @@ __device__ __forceinline__ void load_corner(const PLMeta &m, uint32_t p, const V
 #pragma unroll
         for (int f = 0; f < F; ++f) out[f] = __ldg(grid + e + f);
     }
+}
+
+// All 8 corner element offsets and trilinear weights of one 3-D level with few instructions: dense strides / hash terms
+// are formed once and combined per corner (uint32 wrap-around arithmetic, identical to corner_index<3>), and the
+// modulus is a mask when the table size is a power of two.  Weights keep the (wx*wy)*wz rounding order.
+__device__ __forceinline__ void level_corners3(const PLMeta &m, uint32_t p, const float (&xs)[3], uint32_t (&idx)[8], float (&w)[8]) {
+    const uint32_t rx = m.res[p][0], ry = m.res[p][1], rz = m.res[p][2];
+    uint32_t cell[3];
+    float fr[3];
+    {
+        const float sx = (float)(rx - 2u), sy = (float)(ry - 2u), sz = (float)(rz - 2u);
+        const float vx = __fmaf_rn(xs[0], sx, 0.5f), vy = __fmaf_rn(xs[1], sy, 0.5f), vz = __fmaf_rn(xs[2], sz, 0.5f);
+        const float fx = floorf(vx), fy = floorf(vy), fz = floorf(vz);
+        cell[0] = (uint32_t)fx; cell[1] = (uint32_t)fy; cell[2] = (uint32_t)fz;
+        fr[0] = vx - fx; fr[1] = vy - fy; fr[2] = vz - fz;
+    }
+    const float wx0 = __fsub_rn(1.f, fr[0]), wy0 = __fsub_rn(1.f, fr[1]), wz0 = __fsub_rn(1.f, fr[2]);
+    const float w00 = __fmul_rn(wx0, wy0), w10 = __fmul_rn(fr[0], wy0), w01 = __fmul_rn(wx0, fr[1]), w11 = __fmul_rn(fr[0], fr[1]);
+    w[0] = __fmul_rn(w00, wz0); w[1] = __fmul_rn(w10, wz0); w[2] = __fmul_rn(w01, wz0); w[3] = __fmul_rn(w11, wz0);
+    w[4] = __fmul_rn(w00, fr[2]); w[5] = __fmul_rn(w10, fr[2]); w[6] = __fmul_rn(w01, fr[2]); w[7] = __fmul_rn(w11, fr[2]);
+    const uint32_t nf = m.nfeat[p], base = m.base[p];
+    if (m.is_hash & (1u << p)) {
+        const uint32_t hx0 = cell[0], hx1 = cell[0] + 1u;
+        const uint32_t hy0 = cell[1] * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = cell[2] * 805459861u, hz1 = hz0 + 805459861u;
+        const uint32_t a00 = hy0 ^ hz0, a10 = hy1 ^ hz0, a01 = hy0 ^ hz1, a11 = hy1 ^ hz1;
+        uint32_t h[8] = {hx0 ^ a00, hx1 ^ a00, hx0 ^ a10, hx1 ^ a10, hx0 ^ a01, hx1 ^ a01, hx0 ^ a11, hx1 ^ a11};
+        const uint32_t mask = m.mask[p], size = m.size[p];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = (mask ? (h[c] & mask) : (h[c] % size)) * nf + base;
+    } else {
+        const uint32_t sy_ = rz, sx_ = ry * rz;
+        const uint32_t b0 = (cell[0] * ry + cell[1]) * rz + cell[2];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = (b0 + ((c & 1) ? sx_ : 0u) + ((c & 2) ? sy_ : 0u) + ((c & 4) ? 1u : 0u)) * nf + base;
+    }
+}
+
+// one level's two fp16 features of a point, accumulated in fp16 over the corners (reference semantics), as a packed half2
+__device__ __forceinline__ uint32_t level_feat2(const __half *__restrict__ grid, const uint32_t (&idx)[8], const float (&w)[8]) {
+    uint32_t raw[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) raw[c] = ld_nc_u32(grid + idx[c]);
+    __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2 *>(&raw[c]));
+        acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w[c], v.x), __fmul_rn(w[c], v.y)));
+    }
+    return *reinterpret_cast<uint32_t *>(&acc);
 }
 
 // grad[dst .. dst+F) += g[f] * w, fp32, fire-and-forget vector reductions (8-byte aligned: F even, offsets even).

@@ -171,13 +171,26 @@ class _FusedSDF(autograd.Function):
         d_W1, d_b1 = torch.zeros(w1s, dtype=torch.float32, device=dev), torch.zeros(b1s, dtype=torch.float32, device=dev)
         d_W2, d_b2 = torch.zeros(w2s, dtype=torch.float32, device=dev), torch.zeros(b2s, dtype=torch.float32, device=dev)
         d_sdf = d_sdf.contiguous().float()
+        # Most boundary points of a NeuS ray carry an exactly-zero cotangent (saturated sigmoid far from the surface, samples
+        # behind the early-stop): only the others are recomputed (the reference's scatter kernel skips them one by one).
+        keep = d_sdf.nonzero().squeeze(-1)
+        n = keep.numel()
+        if n == 0:
+            return None, None, None, d_grid, d_W1, d_b1, d_W2, d_b2
+        sparse = n < 0.9 * ctx.n
+        if sparse:
+            d_sdf = d_sdf[keep]
         if isinstance(ctx.pts, tuple):
             ridx, t, rays_o, rays_d = ctx.pts
+            if sparse:
+                ridx, t = ridx[keep], t[keep]
             args = (None, L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"), L.ptr(ridx, "i64"), L.ptr(t, "f32"))
         else:
-            args = (L.ptr(ctx.pts, "f32"), None, None, None, None)
-        with L.KERNEL_TIMER.time("fused_sdf_bwd", ctx.n):
-            L.check(L.lib().nsb_fused_sdf_bwd(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), *args, L.ptr(d_sdf, "f32"), L.c_i64(ctx.n),
+            pts = ctx.pts[keep] if sparse else ctx.pts
+            args = (L.ptr(pts, "f32"), None, None, None, None)
+        n = n if sparse else ctx.n
+        with L.KERNEL_TIMER.time("fused_sdf_bwd", n):
+            L.check(L.lib().nsb_fused_sdf_bwd(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), *args, L.ptr(d_sdf, "f32"), L.c_i64(n),
                                               L.c_i32(ctx.max_level), L.ptr(d_grid), L.ptr(d_W1), L.ptr(d_b1), L.ptr(d_W2), L.ptr(d_b2),
                                               L.stream_ptr()), "fused_sdf_bwd")
         return None, None, None, d_grid, d_W1, d_b1, d_W2, d_b2
