@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rayschunk", type=int, default=65536)
+    ap.add_argument("--rayschunk", type=int, default=H * W, help="rays per render call (default: the whole frame in one call)")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step (default: the full 800x600 frame)")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
