@@ -179,7 +179,7 @@ k_packed_invert_cdf(const float *__restrict__ bins, const float *__restrict__ cd
         else {
             const float c0 = cc[pos - 1], pmf = __fsub_rn(cc[pos], c0);
             if (pmf < 1.0e-5f) r = bb[pos - 1];
-            else r = __fadd_rn(bb[pos - 1], __fmul_rn(__fdiv_rn(__fsub_rn(uu, c0), pmf), __fsub_rn(bb[pos], bb[pos - 1])));
+            else r = __fmaf_rn(__fdiv_rn(__fsub_rn(uu, c0), pmf), __fsub_rn(bb[pos], bb[pos - 1]), bb[pos - 1]);   // nvcc fuses the reference's b0 + t*(b1-b0)
         }
         samples[t] = r;
     }
@@ -317,7 +317,7 @@ k_interleave_linstep(const float *__restrict__ start, const int64_t *__restrict_
         const int64_t n = num_steps[p], b = cum[p] - n;
         const float s0 = start[p], st = step ? step[p] : step_scalar;
         for (int64_t j = lane; j < n; j += 32) {
-            out[b + j] = __fadd_rn(s0, __fmul_rn((float)j, st));
+            out[b + j] = __fmaf_rn((float)j, st, s0);          // one FMA, as nvcc compiles the reference's start + j*step
             if (nidx) nidx[b + j] = p;
         }
     }

@@ -29,9 +29,9 @@ EXTS = {
                                "csrc/occ_grid/src/occ_grid.cpp"],
                       include=["csrc/occ_grid/include", "csrc/forest"], nvcc=HALF_ON + COMMON),
     # AT_DISPATCH_ALL_TYPES_AND_HALF was removed from ATen (torch >= 2.x spells it AT_DISPATCH_ALL_TYPES_AND(kHalf, ...));
-    # the alias is supplied on the command line so that the reference source compiles unmodified.
+    # the alias is force-included (oracle/ref_compat.h) so that the reference source compiles unmodified.
     "_pack_ops": dict(sources=["csrc/pack_ops/pack_ops_cuda.cu", "csrc/pack_ops/pack_ops.cpp"], include=["csrc/pack_ops"],
-                      nvcc=HALF_OFF + COMMON + ["-DAT_DISPATCH_ALL_TYPES_AND_HALF(TYPE,NAME,...)=AT_DISPATCH_ALL_TYPES_AND(at::ScalarType::Half,TYPE,NAME,__VA_ARGS__)"]),
+                      nvcc=HALF_OFF + COMMON + ["-include", os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_compat.h")]),
     "_shencoder": dict(sources=["externals/shencoder/shencoder.cu", "externals/shencoder/bindings.cpp"], include=["externals/shencoder"],
                        nvcc=HALF_ON + COMMON),
     "_lotd": dict(sources=["csrc/lotd/src/compile_split_1.cu", "csrc/lotd/src/compile_split_2.cu", "csrc/lotd/src/compile_split_3.cu",

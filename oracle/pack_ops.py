@@ -44,7 +44,10 @@ def interleave_linstep(start, num_steps, step_size, return_idx=True):
     step = step.astype(s.dtype)
     nidx = np.repeat(np.arange(n.size, dtype=np.int64), n)
     j = np.concatenate([np.arange(k, dtype=np.int64) for k in n]) if n.size else np.zeros(0, np.int64)
-    out = (s[nidx] + (j.astype(s.dtype) * step[nidx]).astype(s.dtype)).astype(s.dtype)
+    if s.dtype == np.float32:   # start + j*step is one fused multiply-add in the compiled reference kernel (fp64 product is exact)
+        out = (s[nidx].astype(np.float64) + j.astype(np.float64) * step[nidx].astype(np.float64)).astype(np.float32)
+    else:
+        out = (s[nidx] + (j.astype(s.dtype) * step[nidx]).astype(s.dtype)).astype(s.dtype)
     return torch.from_numpy(out), (torch.from_numpy(nidx) if return_idx else None)
 
 
@@ -217,7 +220,9 @@ def packed_invert_cdf(bins, cdfs, u_vals, pack_infos):
                     samples[p, i] = bb[pos - 1]
                 else:
                     t = dt(dt(u - cc[pos - 1]) / pmf)
-                    samples[p, i] = dt(bb[pos - 1] + dt(t * dt(bb[pos] - bb[pos - 1])))
+                    # b0 + t*(b1-b0) is one fused multiply-add in the compiled reference kernel (checked on the GPU against
+                    # oracle/_ref): the fp32 x fp32 product is exact in fp64, so one fp64 add + one rounding reproduces it
+                    samples[p, i] = dt(np.float64(t) * np.float64(dt(bb[pos] - bb[pos - 1])) + np.float64(bb[pos - 1]))
     return torch.from_numpy(samples), torch.from_numpy(bidx)
 
 
