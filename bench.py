@@ -194,17 +194,37 @@ def run_reference(args, rank):
         "gpu_launches": 0}), flush=True)
 
 
+def use_reference_cuda_kernels():
+    """route the SAME host orchestration through the REFERENCE'S OWN CUDA kernels (oracle/_ref: `_lotd`,
+    `_pack_ops`, `_occ_grid`, `_shencoder` compiled from /root/reference) and switch every fused path off, i.e. the op
+    sequence nr3d_lib executes (16-level gather kernels, autocast cuBLAS MLPs, one-thread-per-pack pack_ops, fp16 atomics).
+    Only used by `--impl reference-cuda` and the `reference_cuda` field; never by the product path."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    mods = {n: build_ref.load(n) for n in ("_lotd", "_pack_ops", "_occ_grid", "_shencoder")}
+    if any(m is None for m in mods.values()):
+        return False
+    import neuralsim_b200.fields.encoding as E
+    import neuralsim_b200.fields.networks as NW
+    import neuralsim_b200.graphics.pack_ops as GP
+    import neuralsim_b200.graphics.raymarch as GR
+    E._backend, GP._backend, GR._backend, NW._shencoder = mods["_lotd"], mods["_pack_ops"], mods["_occ_grid"], mods["_shencoder"]
+    NW.LoTDSDF._fusable = lambda self: False
+    return True
+
+
 # ---------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--rayschunk", type=int, default=H * W, help="rays per render call (default: the whole frame in one call)")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step (default: the full 800x600 frame)")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -223,6 +243,8 @@ def main():
 
     from neuralsim_b200 import _lib
     from neuralsim_b200.renderer import SingleVolumeRenderer
+    if args.impl == "reference-cuda" and not use_reference_cuda_kernels():
+        raise SystemExit("bench.py: oracle/_ref is not built (python oracle/build_ref.py in the build container)")
     model = build_model(device).train()
     renderer = SingleVolumeRenderer(dict(near=0.01, rayschunk=0)).train()
     flat, params = flat_grad_views(model)
@@ -328,6 +350,20 @@ def main():
                 "h2d_bytes_per_step": int(2 * n_rays * 3 * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof,
     }
+    if args.impl == "reference-cuda":
+        line["impl"] = "reference-cuda"
+        line["gpu_launches"] = 0
+        line["config"]["note"] = "the reference's own CUDA kernels (oracle/_ref) under the same orchestration; no neuralsim_b200 kernel runs"
+    elif world == 1 and not args.no_ref_cuda:
+        # B1 of BASELINE.md, measured in a child process so that none of its module patching can leak into this arm
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--steps", "2", "--warmup", "2",
+                                "--no-cpu-baseline", "--rayschunk", str(args.rayschunk)], capture_output=True, text=True, timeout=600)
+            rl = json.loads(r.stdout.strip().splitlines()[-1])
+            line["reference_cuda"] = {"value": rl["value"], "unit": "Mrays/s", "ms_per_step": rl["ms_per_step"], "e2e": rl["e2e"]["value"],
+                                      "what": "reference nr3d_lib CUDA kernels compiled from /root/reference (oracle/_ref), same B200, same workload"}
+        except Exception as ex:
+            line["reference_cuda"] = {"unavailable": repr(ex)[:200]}
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(args.ref_rays)

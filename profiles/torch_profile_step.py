@@ -16,13 +16,14 @@ r = SingleVolumeRenderer(dict(near=0.01)).train()
 flat, params = bench.flat_grad_views(model)
 o, d = bench.pinhole_rays(bench.H, bench.W, bench.orbit(0, 8))
 o, d = o.to(dev), d.to(dev)
-ha = torch.zeros(65536, 4, device=dev)
+CH = int(os.environ.get("CHUNK", 480000))
+ha = torch.zeros(CH, 4, device=dev)
 
 
 def step():
     flat.zero_()
-    for s in range(0, o.shape[0], 65536):
-        e = min(s + 65536, o.shape[0])
+    for s in range(0, o.shape[0], CH):
+        e = min(s + CH, o.shape[0])
         out = r.render(model, o[s:e], d[s:e], rays_h_appear=ha[:e - s])["rendered"]
         loss = bench.loss_of(out) * ((e - s) / o.shape[0])
         if loss.requires_grad:
