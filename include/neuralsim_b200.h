@@ -184,6 +184,69 @@ int nsb_fused_sdf_bwd(const nsb_lotd_meta *meta_host, const void *params_half, c
                       const float *d_sdf, int64_t n, int32_t max_level, float *d_grid, float *d_W1, float *d_b1,
                       float *d_W2, float *d_b2, void *stream);
 
+/* ---------------------------------------------------------------- fused per-ray NeuS stages (csrc/neus_fused.cu)
+ * One warp per ray (pack).  Each entry point replaces a chain of the reference's Python-level calls with one launch;
+ * the pack_ops entry points above remain the drop-in for `_pack_ops` itself.
+ *
+ * nsb_neus_upsample_cdf: cdf[S] = packed_div(packed_cumsum(packed_alpha_to_vw(alpha), exclusive), max(last, 1e-5)) with
+ *   alpha = neus_packed_sdf_to_alpha(sdf, inv_s) or, if use_estimate_alpha, neus_packed_sdf_to_upsample_alpha(sdf, depth, inv_s)
+ *   (nr3d_lib/graphics/neus/neus_ray_query.py:873-884, neus_utils.py:88-111,164-188). */
+int nsb_neus_upsample_cdf(const float *sdf, const float *depth, const int64_t *pack_infos, int64_t n_packs, float inv_s,
+                          int use_estimate_alpha, float early_stop_eps, float alpha_thre, float *cdf, void *stream);
+/* packed_invert_cdf (pack_ops_cuda.cu:1634-1682) with ONE u[n_samples] row shared by every pack -> samples[n_packs, n_samples]
+ * (what packed_sample_cdf(perturb=False) feeds it, graphics/raysample.py:38-61). */
+int nsb_packed_invert_cdf_shared_u(const float *bins, const float *cdfs, const float *u, const int64_t *pack_infos, int64_t n_packs,
+                                   int32_t n_samples, float *samples, void *stream);
+/* alpha[S] = neus_packed_sdf_to_alpha(sdf, *inv_s_dev) and, in the same pass, the compression selector / kept-count per pack
+ * of packed_volume_render_compression (pack_ops.py:286-291).  inv_s is read from device memory (no host sync). */
+int nsb_neus_alpha_forward(const float *sdf, const int64_t *pack_infos, int64_t n_packs, const float *inv_s_dev, float early_stop_eps,
+                           float alpha_thre, float *alpha, uint8_t *selector, int64_t *num_steps, void *stream);
+/* adjoint of the above: d_sdf[S] (written), d_inv_s[1] (accumulated; caller zero-fills). */
+int nsb_neus_alpha_backward(const float *sdf, const int64_t *pack_infos, int64_t n_packs, const float *inv_s_dev, const float *d_alpha,
+                            float *d_sdf, float *d_inv_s, void *stream);
+/* Volume integration of one packed buffer (app/renderers/single_volume_renderer.py:73-102): vw = alpha_to_vw(alpha);
+ * mask = sum vw; depth = sum vw t / (mask + 1e-10) (or sum vw t); rgb_out = sum vw rgb; nablas_out = sum vw nablas.
+ * rgb / nablas ([K,3]) may be NULL. */
+int nsb_composite_forward(const float *alpha, const float *t, const float *rgb, const float *nablas, const int64_t *pack_infos,
+                          int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth, float *vw, float *mask,
+                          float *depth, float *rgb_out, float *nablas_out, void *stream);
+/* its adjoint; any of g_* may be NULL (= zero cotangent); writes d_alpha[K], d_rgb[K,3], d_nablas[K,3]. */
+int nsb_composite_backward(const float *alpha, const float *t, const float *rgb, const float *nablas, const float *vw,
+                           const int64_t *pack_infos, int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth,
+                           const float *mask, const float *depth, const float *g_mask, const float *g_depth, const float *g_rgb,
+                           const float *g_nablas, const float *g_vw, float *d_alpha, float *d_rgb, float *d_nablas, void *stream);
+
+/* ---------------------------------------------------------------- fused colour / normal query (csrc/color_tc.cu)
+ * The whole LoTDNeuS.forward of the reference for packed samples (nr3d_lib/models/fields/neus/lotd_neus.py:141-167 =
+ * LoTDSDF.forward_sdf_nablas, lotd_sdf.py:201-257, + RadianceNet.forward, mlp_nerf.py:267-289) as one tcgen05 kernel, and
+ * its backward including the second-order pass through nablas (LoTDFunctionBwdDydx.backward, lotd.py:193-268) as two.
+ * All weight pointers are fp16 device images of the fp32 masters (what autocast feeds the GEMMs). */
+typedef struct nsb_color_net {
+    const void *W1, *b1, *W2, *b2;            /* sdf decoder: [width x 32], [width], [1 x width], [1]              */
+    const void *R1, *rb1, *R2, *rb2, *R3, *rb3; /* radiance net: [rw x rad_in], [rw], [rw x rw], [rw], [3 x rw], [3] */
+    int32_t width, rad_width, rad_in, n_appear; /* rad_in = 3 + 16 + 3 + 32 + n_appear ([x, SH4(v), n, h, h_appear]) */
+    float beta;                               /* Softplus beta of the decoder                                      */
+    float nablas_scale[3];                    /* sdf_scale / radius3d_original                                     */
+} nsb_color_net;
+
+/* bytes of ONE saved activation buffer for n points (fp16 tiles of 128 points x 64 columns, core-matrix layout) */
+int64_t nsb_color_tile_bytes(int64_t n);
+/* Points are x[n,3] or rays_o/rays_d[R,3] + ridx[n] (NULL = identity) + t[n]; view_dirs[R,3] and h_appear[R,n_appear] are
+ * indexed by ridx (by the point index when ridx is NULL).  Outputs fp32: sdf[n], nablas[n,3], rgb[n,3], x_out[n,3] (optional).
+ * act_* : four buffers of nsb_color_tile_bytes(n) each kept for the backward, or all NULL for inference. */
+int nsb_fused_color_fwd(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_color_net *net_host, const float *x,
+                        const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, const float *view_dirs,
+                        const float *h_appear, int64_t n, int32_t max_level, float *sdf, float *nablas, float *rgb, float *x_out,
+                        void *act_z, void *act_x, void *act_y1, void *act_y2, void *stream);
+/* Cotangents g_sdf[n], g_nablas[n,3], g_rgb[n,3] (each may be NULL = zero); dh_scratch[n,32] fp32 workspace.
+ * All gradient outputs are fp32 and ACCUMULATED into (caller zero-fills); d_R* use the reference's column order. */
+int nsb_fused_color_bwd(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_color_net *net_host, const float *x,
+                        const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n, int32_t max_level,
+                        const void *act_z, const void *act_x, const void *act_y1, const void *act_y2, const float *rgb,
+                        const float *g_sdf, const float *g_nablas, const float *g_rgb, float *dh_scratch, float *d_grid, float *d_W1,
+                        float *d_b1, float *d_W2, float *d_b2, float *d_R1, float *d_rb1, float *d_R2, float *d_rb2, float *d_R3,
+                        float *d_rb3, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,12 @@ class SdfDecoderC(ctypes.Structure):
                 ("width", ctypes.c_int32), ("beta", ctypes.c_float)]
 
 
+class ColorNetC(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("W1", "b1", "W2", "b2", "R1", "rb1", "R2", "rb2", "R3", "rb3")] + [
+        ("width", ctypes.c_int32), ("rad_width", ctypes.c_int32), ("rad_in", ctypes.c_int32), ("n_appear", ctypes.c_int32),
+        ("beta", ctypes.c_float), ("nablas_scale", ctypes.c_float * 3)]
+
+
 _lib = None
 
 
@@ -46,6 +52,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.nsb_last_error.restype = ctypes.c_char_p
         _lib.nsb_launch_count.restype = ctypes.c_uint64
+        _lib.nsb_color_tile_bytes.restype = ctypes.c_int64
     return _lib
 
 

@@ -7,16 +7,20 @@ State-dict names follow the reference so checkpoints keep loading (SURVEY.md §9
 """
 from __future__ import annotations
 
+import ctypes
 from types import SimpleNamespace
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..graphics import neus as neus_graphics, neus_fused
 from ..graphics.neus import neus_ray_query_march_occ_multi_upsample_compressed
 from ..graphics.nerf import packed_alpha_to_vw, ray_alpha_to_vw
 from ..graphics.pack_ops import packed_div, packed_sum
+from .. import _lib as L
 from .accel import OccGridAccel
+from .fused_color import fused_color
 from .networks import LoTDSDF, RadianceNet, VarSingleMixLinear
 from .space import AABBSpace
 
@@ -72,6 +76,37 @@ class LoTDNeuS(nn.Module):
             x = torch.addcmul(rays_o[ridx].unsqueeze(-2), rays_d[ridx].unsqueeze(-2), t.unsqueeze(-1)).flatten(0, -2)
             return dict(sdf=self.forward_sdf(x)["sdf"].view(t.shape))
         return self.forward_sdf(torch.addcmul(rays_o[ridx], rays_d[ridx], t.unsqueeze(-1)))
+
+    # ---- fused colour query (csrc/color_tc.cu)
+    def _color_fusable(self):
+        from .networks import SHEncoder
+        r, b = self.radiance_net, self.radiance_net.blocks
+        return (self.implicit_surface._fusable() and r.use_pos and r.use_view_dirs and r.use_nablas and r.use_extra_feat
+                and isinstance(r.embed_fn_view, SHEncoder) and r.embed_fn_view.degree == 4 and b.D == 2 and not b.skips and b.dtype == torch.half
+                and all(isinstance(l.activation, nn.ReLU) for l in b.layers[:2]) and isinstance(b.layers[2].activation, nn.Sigmoid)
+                and b.layers[0].out_features <= 64 and b.layers[1].out_features <= 64 and b.layers[1].in_features == b.layers[0].out_features
+                and 54 <= b.layers[0].in_features <= 62 and all(l.bias is not None for l in b.layers))
+
+    def _fused_color_state(self):
+        """(fp16 table, nsb_color_net, the fp16 tensors it points at) -- rebuilt when a master changed."""
+        s, b = self.implicit_surface, self.radiance_net.blocks.layers
+        grid16, _dec = s._fused_state()
+        ps = [s.decoder.layers[0].weight, s.decoder.layers[0].bias, s.decoder.layers[1].weight, s.decoder.layers[1].bias,
+              b[0].weight, b[0].bias, b[1].weight, b[1].bias, b[2].weight, b[2].bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        cache = getattr(self, "_color_cache", None)
+        if cache is None or cache[0] != key:
+            t = [p.detach().to(torch.half).contiguous() for p in ps]
+            fac = (s.sdf_scale / s.radius3d_original).float().tolist()
+            net = L.ColorNetC(*[x.data_ptr() for x in t], s.decoder.layers[0].out_features, b[0].out_features, b[0].in_features,
+                              b[0].in_features - 54, float(s.decoder.layers[0].activation.beta), (ctypes.c_float * 3)(*fac))
+            cache = self._color_cache = (key, t, net)
+        return grid16, cache[2], cache[1]
+
+    def forward_on_rays(self, ridx, t, rays_o, rays_d, view_dirs, rays_h_appear=None, *, nablas_has_grad=True):
+        """LoTDNeuS.forward at x = o[ridx] + d[ridx] t with per-ray view_dirs / h_appear, as one fused op (fields/fused_color.py)."""
+        return fused_color(self, ridx, t, rays_o, rays_d, view_dirs, rays_h_appear if self.use_h_appear else None,
+                           nablas_has_grad=nablas_has_grad)
 
     @torch.no_grad()
     def query_sdf(self, x):
@@ -203,6 +238,22 @@ def volume_integration(volume_buffer, rendered, training=True, depth_use_normali
     """vw = alpha_to_vw(alpha); mask = sum vw; depth = sum vw/(mask+1e-10) t; rgb = sum vw rgb; normals = sum vw nablas
     (single_volume_renderer.py:73-102 / renderer_mixin.py:396-439).  Writes into `rendered` at rays_inds_hit."""
     hit = volume_buffer["rays_inds_hit"]
+    if volume_buffer["type"] == "packed" and neus_graphics.FUSED_STAGES:
+        # one kernel: weights + the four per-ray sums (+ one adjoint kernel), csrc/neus_fused.cu
+        nab = volume_buffer.get(nablas_key) if "normals_volume" in rendered else None
+        if nab is not None and not training:
+            nab = F.normalize(nab.clamp(-1, 1), dim=-1)
+        rgb = volume_buffer.get("rgb") if "rgb_volume" in rendered else None
+        vw, m, d, c, nn_ = neus_fused.composite(volume_buffer["opacity_alpha"], volume_buffer["t"], volume_buffer["pack_infos_hit"],
+                                                 rgb=rgb, nablas=nab, normalize_depth=depth_use_normalized_vw)
+        volume_buffer["vw"] = vw
+        rendered["mask_volume"] = rendered["mask_volume"].index_put((hit,), m)
+        rendered["depth_volume"] = rendered["depth_volume"].index_put((hit,), d)
+        if c is not None:
+            rendered["rgb_volume"] = rendered["rgb_volume"].index_put((hit,), c)
+        if nn_ is not None:
+            rendered["normals_volume"] = rendered["normals_volume"].index_put((hit,), nn_)
+        return rendered
     if volume_buffer["type"] == "batched":
         vw = ray_alpha_to_vw(volume_buffer["opacity_alpha"])
         vw_sum = vw.sum(-1)

@@ -18,6 +18,11 @@ from .nerf import packed_alpha_to_vw, packed_volume_render_compression, ray_alph
 from .pack_ops import (get_pack_infos_from_batch, merge_two_batch_a_includes_b, merge_two_packs_sorted_aligned,
                        packed_cumsum, packed_diff, packed_div)
 from .raysample import batch_sample_step_linear, packed_sample_cdf
+from . import neus_fused
+
+# True: the per-ray stages run as the fused kernels of csrc/neus_fused.cu; False: as the reference's chain of
+# pack_ops / elementwise calls (same maths; kept for the parity tests and as documentation of what is fused).
+FUSED_STAGES = True
 
 __all__ = ["neus_cdf", "neus_ray_cdf_to_alpha", "neus_ray_sdf_to_alpha", "neus_ray_sdf_to_vw", "neus_packed_cdf_to_alpha",
            "neus_packed_sdf_to_alpha", "neus_packed_sdf_to_upsample_alpha", "neus_ray_sdf_to_upsample_alpha",
@@ -88,6 +93,13 @@ def neus_ray_sdf_to_upsample_alpha(sdf, depth_samples, inv_s):
 # ---------------------------------------------------------------------------------------------------------------------
 def _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths, *, nablas_has_grad,
                       with_rgb, with_normal, dtype):
+    if (FUSED_STAGES and with_rgb and view_dirs is not None and getattr(model, "_color_fusable", lambda: False)()
+            and not (rays_h_appear is not None and rays_h_appear.requires_grad) and not depths.requires_grad):
+        out = model.forward_on_rays(ridx_all, depths, rays_o, rays_d, view_dirs, rays_h_appear, nablas_has_grad=nablas_has_grad)
+        volume_buffer["net_x"] = out["x"]
+        volume_buffer["nablas"] = out["nablas"].to(dtype)
+        volume_buffer["rgb"] = out["rgb"].to(dtype)
+        return
     x = torch.addcmul(rays_o[ridx_all], rays_d[ridx_all], depths.unsqueeze(-1))
     kw = dict(x=x, nablas_has_grad=nablas_has_grad, with_rgb=with_rgb, with_normal=with_normal)
     if rays_h_appear is not None:
@@ -146,15 +158,21 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
             sdf = model.forward_sdf(marched.samples)["sdf"].to(dtype)
             fine_stages = []
             for i, factor in enumerate(upsample_inv_s_factors):
-                if upsample_use_estimate_alpha:
-                    alpha = neus_packed_sdf_to_upsample_alpha(sdf, depth_samples, upsample_inv_s * factor, pack_infos)
+                if FUSED_STAGES:
+                    cdf = neus_fused.upsample_cdf(sdf, depth_samples, pack_infos, upsample_inv_s * factor, upsample_use_estimate_alpha)
                 else:
-                    alpha = neus_packed_sdf_to_alpha(sdf, upsample_inv_s * factor, pack_infos)
-                vw = packed_alpha_to_vw(alpha, pack_infos)
-                cdf = packed_cumsum(vw, pack_infos, exclusive=True)
-                norm = cdf[pack_infos[:, 0] + pack_infos[:, 1] - 1].clamp_min(1e-5)
-                cdf = packed_div(cdf, norm, pack_infos)
-                fine = packed_sample_cdf(depth_samples, cdf, pack_infos, num_fine[i], perturb=perturb)[0]
+                    if upsample_use_estimate_alpha:
+                        alpha = neus_packed_sdf_to_upsample_alpha(sdf, depth_samples, upsample_inv_s * factor, pack_infos)
+                    else:
+                        alpha = neus_packed_sdf_to_alpha(sdf, upsample_inv_s * factor, pack_infos)
+                    vw = packed_alpha_to_vw(alpha, pack_infos)
+                    cdf = packed_cumsum(vw, pack_infos, exclusive=True)
+                    norm = cdf[pack_infos[:, 0] + pack_infos[:, 1] - 1].clamp_min(1e-5)
+                    cdf = packed_div(cdf, norm, pack_infos)
+                if FUSED_STAGES and not perturb:
+                    fine = neus_fused.sample_cdf_uniform(depth_samples, cdf, pack_infos, num_fine[i])
+                else:
+                    fine = packed_sample_cdf(depth_samples, cdf, pack_infos, num_fine[i], perturb=perturb)[0]
                 fine_stages.append(fine)
                 if n_stage > 1:
                     pinfo_fine = get_pack_infos_from_batch(n_hit, num_fine[i], device=device)
@@ -198,8 +216,11 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
         depths_1_packed[pidx0], depths_1_packed[pidx1] = depths_coarse_1, depths_1
         depths_packed = depths_1_packed + packed_diff(depths_1_packed, pack_infos) / 2.
         sdf_b = model.forward_sdf_on_rays(ridx_all, depths_1_packed, rays_o, rays_d)["sdf"].to(dtype)
-        alpha_packed = neus_packed_sdf_to_alpha(sdf_b, forward_inv_s, pack_infos)
-        nidx_useful, pack_infos_useful, pidx_useful = packed_volume_render_compression(alpha_packed, pack_infos)
+        if FUSED_STAGES:
+            alpha_packed, nidx_useful, pack_infos_useful, pidx_useful = neus_fused.neus_alpha_compress(sdf_b, forward_inv_s, pack_infos)
+        else:
+            alpha_packed = neus_packed_sdf_to_alpha(sdf_b, forward_inv_s, pack_infos)
+            nidx_useful, pack_infos_useful, pidx_useful = packed_volume_render_compression(alpha_packed, pack_infos)
         if nidx_useful.numel() == 0:
             return empty, {}
         ridx_all, depths_packed, alpha_packed = ridx_all[pidx_useful], depths_packed[pidx_useful], alpha_packed[pidx_useful]
