@@ -338,7 +338,8 @@ def main():
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "points_per_launch": gather["units"] / max(gather["launches"], 1), "launches": gather["launches"],
                 "avg_launch_ms": gather["ms"] / max(gather["launches"], 1), "share_of_step": gather["ms"] / (ms_res * args.steps),
-                "per_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kt.items()}}
+                "per_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kt.items()},
+                "per_kernel_points_per_step": {k: v["units"] / args.steps for k, v in kt.items()}}
     line = {
         "metric": "Mrays/sec fwd+bwd", "value": world * n_rays / (ms_res * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",

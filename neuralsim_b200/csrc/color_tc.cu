@@ -46,24 +46,18 @@ __host__ __device__ inline int ref_col(int k, int n_appear) {
     return -1;
 }
 
-// softplus(z; beta) and its derivative as ATen evaluates them in fp32 (threshold 20)
-__device__ __forceinline__ void softplus_sa(float zz, float beta, float inv_beta, float &a, float &s) {
-    const float zb = zz * beta;
-    if (zb > 20.f) { a = zz; s = 1.f; }
-    else { const float e = expf(zb); a = log1pf(e) * inv_beta; s = e / (e + 1.f); }
-}
 
 // d(y_f)/d(x_d) of one level (both features), exactly as k_lotd_fwd<3,2,true,true> computes dy_dx
 __device__ __forceinline__ void level_jacobian(const PLMeta &m, uint32_t p, const float (&xs)[3], const __half *__restrict__ grid,
                                                float (&J0)[3], float (&J1)[3]) {
-    uint32_t idx[8], cell[3];
+    uint32_t cell[8];
     float w[8], fr[3], scale[3];
-    level_corners3(m, p, xs, idx, w);
-    level_pos<3>(m, p, xs, cell, fr, scale);
+    level_cells3(m, p, xs, cell, w, fr, scale);
+    const uint32_t *lp = level_cells_ptr(m, p, grid);
     float2 v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const uint32_t raw = ld_nc_u32(grid + idx[c]);
+        const uint32_t raw = ld_nc_u32(lp + cell[c]);
         v[c] = __half22float2(*reinterpret_cast<const __half2 *>(&raw));
     }
 #pragma unroll
@@ -185,7 +179,7 @@ k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev n
     const uint32_t x_addr = tc::smem_u32(sX), u_addr = tc::smem_u32(sU), w1_addr = tc::smem_u32(sW1), w1t_addr = tc::smem_u32(sW1T);
     const uint32_t r1_addr = tc::smem_u32(sR1), r2_addr = tc::smem_u32(sR2);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const float beta = net.beta, inv_beta = 1.f / net.beta;
+    const SoftplusK spk(net.beta);
     uint32_t phase = 0;
 
     const int64_t n_tiles = (n + kTile - 1) / kTile;
@@ -220,7 +214,7 @@ k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev n
             for (int j = 0; j < 8; ++j) {
                 z[j] = r16f(z[j] + sb1[c * 8 + j]);
                 float a, s;
-                softplus_sa(z[j], beta, inv_beta, a, s);
+                softplus_as(z[j], spk, a, s);
                 out = fmaf(r16f(a), sW2[c * 8 + j], out);
                 uu[j] = sW2[c * 8 + j] * s;
             }
@@ -607,7 +601,7 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
                    w1t_addr = tc::smem_u32(sW1T);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     constexpr uint32_t cDU = 0, cG = 64, cDHZ = 96, cX1 = 128, cX2 = 176;
-    const float beta = net.beta, inv_beta = 1.f / net.beta;
+    const SoftplusK spk(net.beta);
     uint32_t phase = 0;
     bool first_tile = true;
 
@@ -636,7 +630,7 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float a, s;
-                softplus_sa(z[j], beta, inv_beta, a, s);
+                softplus_as(z[j], spk, a, s);
                 uu[j] = sW2[c * 8 + j] * s;
             }
             *reinterpret_cast<uint4 *>(sT + kTileBytes + c * kChunk + tid * 16) = tc::pack8_f16(uu);
@@ -682,9 +676,9 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float a, s;
-                softplus_sa(z[j], beta, inv_beta, a, s);
+                softplus_as(z[j], spk, a, s);
                 const float w2 = sW2[c * 8 + j], d = r16f(du[j]);
-                const float curv = (z[j] * beta > 20.f) ? 0.f : beta * s * (1.f - s);
+                const float curv = (z[j] * spk.k > spk.thr) ? 0.f : spk.beta * s * (1.f - s);
                 dz[j] = d * w2 * curv + dsdf * w2 * s;
                 vv[j] = d * s + dsdf * r16f(a);
             }
@@ -729,10 +723,10 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
             for (uint32_t q = 0; q < 4; ++q) {
                 const uint32_t p = g4 * 4 + q;
                 if (valid && (int)m.level[p] <= max_level) {
-                    uint32_t idx[8], cell[3];
+                    uint32_t cell[8];
                     float w[8], fr[3], sc[3];
-                    level_corners3(m, p, xs, idx, w);
-                    level_pos<3>(m, p, xs, cell, fr, sc);
+                    level_cells3(m, p, xs, cell, w, fr, sc);
+                    float2 *gp = level_grad_ptr(m, p, d_grid);
                     const float g0 = r16f(gg[2 * q]), g1 = r16f(gg[2 * q + 1]);
                     const float h0 = hz[2 * q], h1 = hz[2 * q + 1];
 #pragma unroll
@@ -749,7 +743,7 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
                             wsum += (c & (1 << gd)) ? ww : -ww;
                         }
                         const float a = g0 * wsum + h0 * w[c], b = g1 * wsum + h1 * w[c];
-                        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d_grid + idx[c]), "f"(a), "f"(b) : "memory");
+                        red_add2(gp + cell[c], a, b);
                     }
                 }
             }
@@ -788,7 +782,7 @@ using namespace nsb;
 namespace {
 int make_net(const nsb_color_net *c, const nsb_lotd_meta *meta, PLMeta *m, ColorNetDev *d, const char *who) {
     if (make_plmeta(meta, m)) return 2;
-    NSB_REQUIRE(m->n_pseudo == 16 && m->F == 2 && m->D == 3, "%s: built for 16 x 2 LoTD features in 3-D", who);
+    NSB_REQUIRE(m->n_pseudo == 16 && m->F == 2 && m->D == 3 && plmeta_two_feature_cells(*m), "%s: built for 16 x 2 LoTD features in 3-D", who);
     NSB_REQUIRE(c->width >= 1 && c->width <= 64 && c->rad_width >= 1 && c->rad_width <= 64, "%s: hidden widths must be <= 64", who);
     NSB_REQUIRE(c->n_appear >= 0 && c->n_appear <= 8 && c->rad_in == 54 + c->n_appear,
                 "%s: radiance input must be [x(3), SH deg 4 (16), n(3), h(32), h_appear(<=8)]", who);

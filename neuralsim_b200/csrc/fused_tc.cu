@@ -45,7 +45,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
     const uint32_t idesc = tc::make_idesc(kTile, HW, 0, 0);
     const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const float beta = dec.beta, inv_beta = 1.f / dec.beta;
+    const SoftplusK spk(dec.beta);
     uint32_t phase = 0;
 
     const int64_t n_tiles = (n + kTile - 1) / kTile;
@@ -76,9 +76,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float zz = __half2float(__float2half_rn(z[j] + sb1[c * 8 + j]));
-                const float zb = zz * beta;
-                const float sp = zb > 20.f ? zz : log1pf(expf(zb)) * inv_beta;       // ATen softplus (threshold 20)
-                out = fmaf(__half2float(__float2half_rn(sp)), sW2[c * 8 + j], out);
+                out = fmaf(__half2float(__float2half_rn(softplus_a(zz, spk))), sW2[c * 8 + j], out);
             }
         }
         if (valid) sdf[i] = __half2float(__float2half_rn(out + sb2));
@@ -146,7 +144,7 @@ k_sdf_bwd_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC
     const uint32_t idesc3 = tc::make_idesc(GW, NX, 1, 1);      // X  = G^T . [H|1]   (MN-major operands)
     const uint32_t a_addr = tc::smem_u32(sA), g_addr = tc::smem_u32(sG), b_addr = tc::smem_u32(sB), bt_addr = tc::smem_u32(sBT);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const float beta = dec.beta, inv_beta = 1.f / dec.beta;
+    const SoftplusK spk(dec.beta);
     uint32_t phase = 0;
     bool first_tile = true;
 
@@ -179,10 +177,8 @@ k_sdf_bwd_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float zz = __half2float(__float2half_rn(z[j] + sb1[c * 8 + j]));
-                const float zb = zz * beta;
                 float a, s;
-                if (zb > 20.f) { a = zz; s = 1.f; }
-                else { const float e = expf(zb); a = log1pf(e) * inv_beta; s = e / (e + 1.f); }
+                softplus_as(zz, spk, a, s);
                 da[j] = dd * __half2float(__float2half_rn(a));
                 dz[j] = dd * sW2[c * 8 + j] * s;
             }
@@ -223,15 +219,13 @@ k_sdf_bwd_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC
             for (uint32_t q = 0; q < 4; ++q) {
                 const uint32_t p = g4 * 4 + q;
                 if (active && (int)m.level[p] <= max_level) {
-                    uint32_t idx[8];
+                    uint32_t cell[8];
                     float w[8];
-                    level_corners3(m, p, xs, idx, w);
+                    level_cells3(m, p, xs, cell, w);
+                    float2 *gp = level_grad_ptr(m, p, d_grid);
                     const float g0 = dh[2 * q], g1 = dh[2 * q + 1];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float a = g0 * w[c], b = g1 * w[c];
-                        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d_grid + idx[c]), "f"(a), "f"(b) : "memory");
-                    }
+                    for (int c = 0; c < 8; ++c) red_add2(gp + cell[c], g0 * w[c], g1 * w[c]);
                 }
             }
         }
@@ -276,7 +270,7 @@ extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *pa
                                        int32_t max_level, float *sdf, void *stream, int from_rays) {
     PLMeta m;
     if (make_plmeta(meta, &m)) return 2;
-    NSB_REQUIRE(m.n_pseudo == 16 && m.F == 2 && m.D == 3, "nsb_fused_sdf (tensor-core): built for 16 x 2 LoTD features in 3-D");
+    NSB_REQUIRE(m.n_pseudo == 16 && m.F == 2 && m.D == 3 && plmeta_two_feature_cells(m), "nsb_fused_sdf (tensor-core): built for 16 x 2 LoTD features in 3-D");
     NSB_REQUIRE(dec->width >= 1 && dec->width <= 64, "nsb_fused_sdf (tensor-core): decoder width must be <= 64");
     DecoderDevTC d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2, dec->width,
                    dec->beta};
@@ -297,7 +291,7 @@ extern "C" int nsb_fused_sdf_bwd(const nsb_lotd_meta *meta, const void *params_h
     NSB_REQUIRE(x || (rays_o && rays_d && t), "nsb_fused_sdf_bwd: need x or (rays_o, rays_d, t)");
     PLMeta m;
     if (make_plmeta(meta, &m)) return 2;
-    NSB_REQUIRE(m.n_pseudo == 16 && m.F == 2 && m.D == 3, "nsb_fused_sdf_bwd: built for 16 x 2 LoTD features in 3-D");
+    NSB_REQUIRE(m.n_pseudo == 16 && m.F == 2 && m.D == 3 && plmeta_two_feature_cells(m), "nsb_fused_sdf_bwd: built for 16 x 2 LoTD features in 3-D");
     NSB_REQUIRE(dec->width >= 1 && dec->width <= 64, "nsb_fused_sdf_bwd: decoder width must be <= 64");
     DecoderDevTC d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2, dec->width,
                    dec->beta};

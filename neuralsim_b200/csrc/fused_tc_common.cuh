@@ -23,10 +23,10 @@ __device__ __forceinline__ void gather_row_to_tile(const PLMeta &m, const __half
     for (uint32_t p = 0; p < 16; ++p) {
         uint32_t packed = 0;
         if ((int)m.level[p] <= max_level) {
-            uint32_t idx[8];
+            uint32_t cell[8];
             float w[8];
-            level_corners3(m, p, xs, idx, w);
-            packed = level_feat2(grid, idx, w);
+            level_cells3(m, p, xs, cell, w);
+            packed = level_feat2_cells(level_cells_ptr(m, p, grid), cell, w);
         }
         *reinterpret_cast<uint32_t *>(tile + (p >> 2) * (R * 16) + r * 16 + (p & 3) * 4) = packed;
     }
@@ -50,6 +50,35 @@ __device__ __forceinline__ void load_point(bool from_rays, const float *__restri
     // network space [-1,1] -> table space [0,1] (lotd_encoding.py:165), clamp (lotd.py:60)
 #pragma unroll
     for (int d = 0; d < 3; ++d) xs[d] = fminf(fmaxf(__fmaf_rn(xs[d], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
+}
+
+// Softplus(z; beta) with ATen's threshold (beta z > 20 -> identity) on the SFU: e = 2^(z beta log2 e), a = log2(1 + e) ln2 / beta.
+// ex2.approx / lg2.approx are accurate to ~2^-22 relative; the result is rounded to fp16 (2^-11) right after, and the
+// absolute error (< 1e-7 / beta) is far below the fp16 spacing at every magnitude, so the fp16 activation differs from the
+// expf/log1pf evaluation only in rare round-to-nearest ties (tests: <= 1 fp16 ulp).  13 issue slots per hidden unit instead of ~50.
+struct SoftplusK {
+    float k, thr, out;                       // beta log2(e), 20 log2(e), ln2 / beta
+    float beta;
+    __device__ __forceinline__ explicit SoftplusK(float b) : k(b * 1.4426950408889634f), thr(20.f * 1.4426950408889634f), out(0.6931471805599453f / b), beta(b) {}
+};
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+__device__ __forceinline__ float softplus_a(float zz, const SoftplusK &K) {
+    const float t = zz * K.k;
+    const float e = ex2_approx(t);
+    const float a = lg2_approx(1.f + e) * K.out;
+    return t > K.thr ? zz : a;
+}
+// a = softplus, s = its derivative sigmoid(beta z) (1 above the threshold, as ATen's backward)
+__device__ __forceinline__ void softplus_as(float zz, const SoftplusK &K, float &a, float &s) {
+    const float t = zz * K.k;
+    const float e = ex2_approx(t);
+    const float d = 1.f + e;
+    const bool lin = t > K.thr;
+    a = lin ? zz : lg2_approx(d) * K.out;
+    s = lin ? 1.f : e * rcp_approx(d);
 }
 
 // W1 [width x 32] (fp16, row-major) -> chunk-major [64 x 32] B tile, rows >= width zero

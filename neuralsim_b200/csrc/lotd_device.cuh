@@ -158,6 +158,82 @@ __device__ __forceinline__ void level_corners3(const PLMeta &m, uint32_t p, cons
     }
 }
 
+// ---- fast path of the fused kernels: every level carries 2 features per cell (one cell == one 32-bit word of the fp16
+// table, one float2 of the fp32 gradient), so a corner is addressed as `level_pointer + cell` with ONE wide multiply-add.
+// floor() is taken with the 2^23 trick (v in [0.5, 2^22): fadd.rm(v, 2^23) = 2^23 + floor(v), the integer sits in the
+// mantissa) -- two full-rate FADDs instead of FRND + F2I; `v - floor(v)` is the same fp32 value as in level_corners3.
+__device__ __forceinline__ void level_cells3(const PLMeta &m, uint32_t p, const float (&xs)[3], uint32_t (&cell)[8], float (&w)[8],
+                                             float (&fr)[3], float (&sc)[3]) {
+    const uint32_t rx = m.res[p][0], ry = m.res[p][1], rz = m.res[p][2];
+    sc[0] = (float)(rx - 2u); sc[1] = (float)(ry - 2u); sc[2] = (float)(rz - 2u);
+    const float vx = __fmaf_rn(xs[0], sc[0], 0.5f), vy = __fmaf_rn(xs[1], sc[1], 0.5f), vz = __fmaf_rn(xs[2], sc[2], 0.5f);
+    const float tx = __fadd_rd(vx, 8388608.f), ty = __fadd_rd(vy, 8388608.f), tz = __fadd_rd(vz, 8388608.f);
+    const uint32_t cx = __float_as_uint(tx) - 0x4B000000u, cy = __float_as_uint(ty) - 0x4B000000u, cz = __float_as_uint(tz) - 0x4B000000u;
+    fr[0] = vx - (tx - 8388608.f); fr[1] = vy - (ty - 8388608.f); fr[2] = vz - (tz - 8388608.f);
+    const float wx0 = __fsub_rn(1.f, fr[0]), wy0 = __fsub_rn(1.f, fr[1]), wz0 = __fsub_rn(1.f, fr[2]);
+    const float w00 = __fmul_rn(wx0, wy0), w10 = __fmul_rn(fr[0], wy0), w01 = __fmul_rn(wx0, fr[1]), w11 = __fmul_rn(fr[0], fr[1]);
+    w[0] = __fmul_rn(w00, wz0); w[1] = __fmul_rn(w10, wz0); w[2] = __fmul_rn(w01, wz0); w[3] = __fmul_rn(w11, wz0);
+    w[4] = __fmul_rn(w00, fr[2]); w[5] = __fmul_rn(w10, fr[2]); w[6] = __fmul_rn(w01, fr[2]); w[7] = __fmul_rn(w11, fr[2]);
+    if (m.is_hash & (1u << p)) {
+        const uint32_t hx0 = cx, hx1 = cx + 1u;
+        const uint32_t hy0 = cy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = cz * 805459861u, hz1 = hz0 + 805459861u;
+        const uint32_t a00 = hy0 ^ hz0, a10 = hy1 ^ hz0, a01 = hy0 ^ hz1, a11 = hy1 ^ hz1;
+        const uint32_t h[8] = {hx0 ^ a00, hx1 ^ a00, hx0 ^ a10, hx1 ^ a10, hx0 ^ a01, hx1 ^ a01, hx0 ^ a11, hx1 ^ a11};
+        const uint32_t mask = m.mask[p];
+        if (mask) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cell[c] = h[c] & mask;
+        } else {
+            const uint32_t size = m.size[p];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cell[c] = h[c] % size;
+        }
+    } else {
+        const uint32_t sy_ = rz, sx_ = ry * rz;
+        const uint32_t b0 = (cx * ry + cy) * rz + cz;
+        cell[0] = b0; cell[1] = b0 + sx_; cell[2] = b0 + sy_; cell[3] = cell[1] + sy_;
+        cell[4] = b0 + 1u; cell[5] = cell[1] + 1u; cell[6] = cell[2] + 1u; cell[7] = cell[3] + 1u;
+    }
+}
+
+__device__ __forceinline__ void level_cells3(const PLMeta &m, uint32_t p, const float (&xs)[3], uint32_t (&cell)[8], float (&w)[8]) {
+    float fr[3], sc[3];
+    level_cells3(m, p, xs, cell, w, fr, sc);
+}
+
+// fp16 table viewed as 32-bit cells of level p / fp32 gradient viewed as float2 cells of level p
+__device__ __forceinline__ const uint32_t *level_cells_ptr(const PLMeta &m, uint32_t p, const __half *grid) {
+    return reinterpret_cast<const uint32_t *>(grid + m.base[p]);
+}
+__device__ __forceinline__ float2 *level_grad_ptr(const PLMeta &m, uint32_t p, float *d_grid) {
+    return reinterpret_cast<float2 *>(d_grid + m.base[p]);
+}
+
+__device__ __forceinline__ uint32_t level_feat2_cells(const uint32_t *__restrict__ lp, const uint32_t (&cell)[8], const float (&w)[8]) {
+    uint32_t raw[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) raw[c] = ld_nc_u32(lp + cell[c]);
+    __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2 *>(&raw[c]));
+        acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w[c], v.x), __fmul_rn(w[c], v.y)));
+    }
+    return *reinterpret_cast<uint32_t *>(&acc);
+}
+
+__device__ __forceinline__ void red_add2(float2 *dst, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(a), "f"(b) : "memory");
+}
+
+// true when every pseudo level is a 2-feature level stored at an even element offset (the fast path's precondition)
+inline bool plmeta_two_feature_cells(const PLMeta &m) {
+    for (uint32_t p = 0; p < m.n_pseudo; ++p)
+        if (m.nfeat[p] != 2u || (m.base[p] & 1u)) return false;
+    return m.F == 2u;
+}
+
 // one level's two fp16 features of a point, accumulated in fp16 over the corners (reference semantics), as a packed half2
 __device__ __forceinline__ uint32_t level_feat2(const __half *__restrict__ grid, const uint32_t (&idx)[8], const float (&w)[8]) {
     uint32_t raw[8];

@@ -121,12 +121,13 @@ def test_render_fused_equals_unfused_chain():
     rays_o, rays_d = oscene.pinhole_rays(36, 48, oscene.orbit_camera(1, 8, radius=3.0, elev_deg=25.0))
     rays_o, rays_d = rays_o.cuda(), rays_d.cuda()
     ren = SingleVolumeRenderer(dict(near=0.01, far=None))
+    h_appear = torch.linspace(-0.5, 0.5, rays_o.shape[0] * 4, device="cuda").view(-1, 4).contiguous()
     outs = {}
     for fused in (True, False):
         G.FUSED_STAGES = fused
         try:
             model.zero_grad(set_to_none=True)
-            ret = ren.render(model, rays_o, rays_d, return_buffer=True)
+            ret = ren.render(model, rays_o, rays_d, rays_h_appear=h_appear, return_buffer=True)
             r = ret["rendered"]
             (r["rgb_volume"].square().sum() + r["depth_volume"].sum() * 0.1 + r["mask_volume"].sum() * 0.3
              + r["normals_volume"].square().sum() * 0.05).backward()
