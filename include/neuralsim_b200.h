@@ -200,21 +200,54 @@ int nsb_packed_invert_cdf_shared_u(const float *bins, const float *cdfs, const f
 /* alpha[S] = neus_packed_sdf_to_alpha(sdf, *inv_s_dev) and, in the same pass, the compression selector / kept-count per pack
  * of packed_volume_render_compression (pack_ops.py:286-291).  inv_s is read from device memory (no host sync). */
 int nsb_neus_alpha_forward(const float *sdf, const int64_t *pack_infos, int64_t n_packs, const float *inv_s_dev, float early_stop_eps,
-                           float alpha_thre, float *alpha, uint8_t *selector, int64_t *num_steps, void *stream);
+                           float alpha_thre, float *alpha, uint8_t *selector, int32_t *num_steps, void *stream);
 /* adjoint of the above: d_sdf[S] (written), d_inv_s[1] (accumulated; caller zero-fills). */
 int nsb_neus_alpha_backward(const float *sdf, const int64_t *pack_infos, int64_t n_packs, const float *inv_s_dev, const float *d_alpha,
                             float *d_sdf, float *d_inv_s, void *stream);
 /* Volume integration of one packed buffer (app/renderers/single_volume_renderer.py:73-102): vw = alpha_to_vw(alpha);
  * mask = sum vw; depth = sum vw t / (mask + 1e-10) (or sum vw t); rgb_out = sum vw rgb; nablas_out = sum vw nablas.
- * rgb / nablas ([K,3]) may be NULL. */
+ * rgb / nablas ([K,3]) may be NULL.  ray_index[n_packs] (or NULL = identity): the per-ray outputs of pack p are written at
+ * slot ray_index[p] of mask / depth / rgb_out / nablas_out (the scatter `rendered[k][rays_inds_hit] = ...` of the renderer). */
 int nsb_composite_forward(const float *alpha, const float *t, const float *rgb, const float *nablas, const int64_t *pack_infos,
-                          int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth, float *vw, float *mask,
-                          float *depth, float *rgb_out, float *nablas_out, void *stream);
+                          int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth, const int64_t *ray_index,
+                          float *vw, float *mask, float *depth, float *rgb_out, float *nablas_out, void *stream);
 /* its adjoint; any of g_* may be NULL (= zero cotangent); writes d_alpha[K], d_rgb[K,3], d_nablas[K,3]. */
 int nsb_composite_backward(const float *alpha, const float *t, const float *rgb, const float *nablas, const float *vw,
                            const int64_t *pack_infos, int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth,
                            const float *mask, const float *depth, const float *g_mask, const float *g_depth, const float *g_rgb,
-                           const float *g_nablas, const float *g_vw, float *d_alpha, float *d_rgb, float *d_nablas, void *stream);
+                           const float *g_nablas, const float *g_vw, const int64_t *ray_index, float *d_alpha, float *d_rgb,
+                           float *d_nablas, void *stream);
+
+/* ---------------------------------------------------------------- glue of the per-ray query (csrc/neus_glue.cu)
+ * nsb_scan_counts: one launch for cumsum + nonzero + stack of the reference's wrappers (occgrid_raymarch.py:60-75,
+ *   pack_ops.py:286-291): first[n] = exclusive prefix sum of counts; info2[n,2] = (first, count) int32 (`packed_info`);
+ *   for the non-zero entries in order: nz_index[j] = i, nz_pack[j] = (first_i, count_i), nz_src[j] = src[i];
+ *   totals[2] = (sum of counts, number of non-zero entries), on the device.  Outputs other than totals may be NULL. */
+int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first, int32_t *info2, int64_t *nz_index, int64_t *nz_pack,
+                    const int64_t *src, int64_t *nz_src, int64_t *totals, void *stream);
+/* merge_two_packs_sorted_aligned (pack_ops.py:529-560) fused with the scatter of the payloads: packs of (dep_a, sdf_a) and rows
+ * of (dep_b, sdf_b)[n_packs, n_b], both sorted by depth -> merged (dep_m, sdf_m) and pack_infos_m.  sdf_* may be NULL. */
+int nsb_merge_sorted_vals(const float *dep_a, const float *sdf_a, const int64_t *pack_infos_a, const float *dep_b, const float *sdf_b,
+                          int64_t n_packs, int32_t n_b, float *dep_m, float *sdf_m, int64_t *pack_infos_m, void *stream);
+/* sort(cat(fine stages)) + merge_two_batch_a_includes_b with the coarse samples + ray ids + interval mid-points
+ * (neus_ray_query.py:907-976): coarse[n_rays, n_coarse] sorted rows; fine[n_hit, n_fine] rows of the rays ridx_hit (sorted,
+ * unique).  -> d1, mid [S], ridx_all [S], pack_infos [n_rays, 2], S = n_rays n_coarse + n_hit n_fine. */
+int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_t n_coarse, const int64_t *ridx_hit, int64_t n_hit, const float *fine,
+                          int32_t n_fine, float *d1, float *mid, int64_t *ridx_all, int64_t *pack_infos, void *stream);
+/* gather of the samples packed_volume_render_compression keeps (pack_ops.py:286-291): slot = first_out[p] + rank inside the pack. */
+int nsb_compact_samples(const uint8_t *selector, const int64_t *pack_infos, const int32_t *first_out, const int32_t *kept, int64_t n_packs,
+                        const int64_t *ridx_all, const float *t, const float *alpha, int64_t *pidx, int64_t *ridx_c, float *t_c,
+                        float *alpha_c, void *stream);
+/* dst[idx[j]] = src[j] (unique idx; adjoint of the gather above). */
+int nsb_scatter_f32(const float *src, const int64_t *idx, int64_t n, float *dst, void *stream);
+/* AABBSpace.ray_test (nr3d_lib/models/spatial/aabb.py:71-99): normalised rays o_n, d_n [n,3], clamped slab interval near / far [n]
+ * and flag[n] = the reference's validity mask.  center3 / radius3 are HOST pointers to 3 floats. */
+int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64_t n, const float *center3, const float *radius3, int has_near,
+                      float near_clip, int has_far, float far_clip, float *o_n, float *d_n, float *near, float *far, int32_t *flag,
+                      void *stream);
+/* rows idx[j] of (o_n, d_n, near, far) -> row j of the compacted outputs. */
+int nsb_gather_rays(const int64_t *idx, int64_t n, const float *o_n, const float *d_n, const float *near, const float *far, float *o_c,
+                    float *d_c, float *near_c, float *far_c, void *stream);
 
 /* ---------------------------------------------------------------- fused colour / normal query (csrc/color_tc.cu)
  * The whole LoTDNeuS.forward of the reference for packed samples (nr3d_lib/models/fields/neus/lotd_neus.py:141-167 =

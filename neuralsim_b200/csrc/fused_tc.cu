@@ -9,11 +9,13 @@
 // All loops over levels / hidden units are rolled on purpose: the first, fully unrolled version was 10k SASS instructions
 // (168 KB) and spent most issue slots in instruction-cache misses (ncu: stall_no_instruction 5.9/issue; profiles/r01_*).
 // W1 is staged once per persistent CTA.  Numerics: the fp16 rounding points of the reference's autocast graph.
+#include <stdlib.h>
+
 #include "fused_tc_common.cuh"
 
 namespace nsb {
 
-template <bool FROM_RAYS>
+template <bool FROM_RAYS, bool FAST_SP = true, bool FAST_CELLS = true>
 __global__ void __launch_bounds__(kTile)
 k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
                const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ridx,
@@ -54,7 +56,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
         const bool valid = i < n;
         float xs[3];
         load_point(FROM_RAYS, x, rays_o, rays_d, ridx, t, i, valid, xs);
-        gather_row_to_tile<kTile>(m, grid, xs, max_level, sA, tid);
+        gather_row_to_tile<kTile, FAST_CELLS>(m, grid, xs, max_level, sA, tid);
         tc::fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncthreads();
         if (tid == 0) {
@@ -76,7 +78,10 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float zz = __half2float(__float2half_rn(z[j] + sb1[c * 8 + j]));
-                out = fmaf(__half2float(__float2half_rn(softplus_a(zz, spk))), sW2[c * 8 + j], out);
+                float sp;
+                if (FAST_SP) sp = softplus_a(zz, spk);
+                else { const float zb = zz * spk.beta; sp = zb > 20.f ? zz : log1pf(expf(zb)) * (1.f / spk.beta); }
+                out = fmaf(__half2float(__float2half_rn(sp)), sW2[c * 8 + j], out);
             }
         }
         if (valid) sdf[i] = __half2float(__float2half_rn(out + sb2));
@@ -277,7 +282,14 @@ extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *pa
     const unsigned grid = persistent_grid(n, 8);           // <= 8 resident CTAs/SM (TMEM: 8 x 64 columns)
     cudaStream_t s = (cudaStream_t)stream;
     const int ml = max_level < 0 ? -1 : max_level;
-    if (from_rays) k_fused_sdf_tc<true><<<grid, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
+    // NSB_SDF_VARIANT (profiling only, profiles/ab_gather.py): bit 0 = libm softplus, bit 1 = generic corner addressing
+    const int variant = getenv("NSB_SDF_VARIANT") ? atoi(getenv("NSB_SDF_VARIANT")) : 0;
+    const int ctas = getenv("NSB_SDF_CTAS") ? atoi(getenv("NSB_SDF_CTAS")) : 8;
+    const unsigned g2 = persistent_grid(n, ctas);
+    if (from_rays && variant == 1) k_fused_sdf_tc<true, false, true><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
+    else if (from_rays && variant == 2) k_fused_sdf_tc<true, true, false><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
+    else if (from_rays && variant == 3) k_fused_sdf_tc<true, false, false><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
+    else if (from_rays) k_fused_sdf_tc<true><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
     else k_fused_sdf_tc<false><<<grid, kTile, 0, s>>>(m, (const __half *)params_half, d, x, nullptr, nullptr, nullptr, nullptr, n, ml, sdf);
     return check_launch("nsb_fused_sdf(tc)");
 }

@@ -16,17 +16,23 @@ constexpr int kTile = 128;
 constexpr int NF = 32, HW = 64;           // features, hidden width (zero padded to 64)
 
 // the 16 levels of one point -> row `r` of a chunk-major [R x >=32] fp16 tile (4 bytes per level)
-template <int R>
+template <int R, bool FAST_CELLS = true>
 __device__ __forceinline__ void gather_row_to_tile(const PLMeta &m, const __half *__restrict__ grid, const float (&xs)[3],
                                                    int max_level, uint8_t *tile, int r) {
 #pragma unroll 1
     for (uint32_t p = 0; p < 16; ++p) {
         uint32_t packed = 0;
         if ((int)m.level[p] <= max_level) {
-            uint32_t cell[8];
             float w[8];
-            level_cells3(m, p, xs, cell, w);
-            packed = level_feat2_cells(level_cells_ptr(m, p, grid), cell, w);
+            if (FAST_CELLS) {
+                uint32_t cell[8];
+                level_cells3(m, p, xs, cell, w);
+                packed = level_feat2_cells(level_cells_ptr(m, p, grid), cell, w);
+            } else {
+                uint32_t idx[8];
+                level_corners3(m, p, xs, idx, w);
+                packed = level_feat2(grid, idx, w);
+            }
         }
         *reinterpret_cast<uint32_t *>(tile + (p >> 2) * (R * 16) + r * 16 + (p & 3) * 4) = packed;
     }

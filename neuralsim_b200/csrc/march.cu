@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
             if (occupied) {
                 if (!first_round) {
                     a.t_starts[base + j] = t0;
-                    a.t_ends[base + j] = t1;
+                    if (a.t_ends) a.t_ends[base + j] = t1;
                     a.ridx[base + j] = (int32_t)i;
                     if (a.gidx) a.gidx[base + j] = gi;
                     if (a.bidx) a.bidx[base + j] = b;
@@ -146,7 +146,7 @@ extern "C" int nsb_ray_marching(int64_t n_rays, const float *rays_o, const float
     NSB_REQUIRE(rays_o && rays_d && t_min && t_max && roi && grid_binary, "nsb_ray_marching: NULL input");
     NSB_REQUIRE(rx > 0 && ry > 0 && rz > 0, "nsb_ray_marching: bad grid resolution");
     if (packed_info == nullptr) NSB_REQUIRE(num_steps, "nsb_ray_marching: first round needs num_steps");
-    else NSB_REQUIRE(t_starts && t_ends && ridx, "nsb_ray_marching: second round needs t_starts/t_ends/ridx");
+    else NSB_REQUIRE(t_starts && ridx, "nsb_ray_marching: second round needs t_starts and ridx (t_ends / gidx / bidx are optional)");
     MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, batch_inds, rx, ry, rz, grid_binary, step_size, max_step_size,
                 dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx};
     cudaStream_t s = (cudaStream_t)stream;

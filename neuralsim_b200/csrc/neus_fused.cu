@@ -124,7 +124,7 @@ k_invert_cdf_shared_u(const float *__restrict__ bins, const float *__restrict__ 
 // ------------------------------------------------------------------------------------------------ render alpha (+ compression)
 __global__ void __launch_bounds__(kNB)
 k_neus_alpha_fwd(const float *__restrict__ sdf, const int64_t *__restrict__ pi, int64_t n_packs, const float *__restrict__ inv_s_p, float eps,
-                 float thre, float *__restrict__ alpha, uint8_t *__restrict__ selector, int64_t *__restrict__ num_steps) {
+                 float thre, float *__restrict__ alpha, uint8_t *__restrict__ selector, int32_t *__restrict__ num_steps) {
     const int lane = threadIdx.x & 31;
     const float inv_s = inv_s_p[0];
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
@@ -180,8 +180,8 @@ k_neus_alpha_bwd(const float *__restrict__ sdf, const int64_t *__restrict__ pi, 
 // ------------------------------------------------------------------------------------------------ compositing
 __global__ void __launch_bounds__(kNB)
 k_composite_fwd(const float *__restrict__ alpha, const float *__restrict__ t, const float *__restrict__ rgb, const float *__restrict__ nab,
-                const int64_t *__restrict__ pi, int64_t n_packs, float eps, float thre, int normalize_depth, float *__restrict__ vw,
-                float *__restrict__ mask, float *__restrict__ depth, float *__restrict__ rgb_out, float *__restrict__ nab_out) {
+                const int64_t *__restrict__ pi, int64_t n_packs, float eps, float thre, int normalize_depth, const int64_t *__restrict__ ray_index,
+                float *__restrict__ vw, float *__restrict__ mask, float *__restrict__ depth, float *__restrict__ rgb_out, float *__restrict__ nab_out) {
     const int lane = threadIdx.x & 31;
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
@@ -207,10 +207,11 @@ k_composite_fwd(const float *__restrict__ alpha, const float *__restrict__ t, co
 #pragma unroll
         for (int c = 0; c < 3; ++c) { sr[c] = warp_sum(sr[c]); sn[c] = warp_sum(sn[c]); }
         if (lane == 0) {
-            mask[p] = sm;
-            depth[p] = normalize_depth ? sd / (sm + 1e-10f) : sd;
-            if (rgb) { rgb_out[p * 3] = sr[0]; rgb_out[p * 3 + 1] = sr[1]; rgb_out[p * 3 + 2] = sr[2]; }
-            if (nab) { nab_out[p * 3] = sn[0]; nab_out[p * 3 + 1] = sn[1]; nab_out[p * 3 + 2] = sn[2]; }
+            const int64_t o = ray_index ? ray_index[p] : p;          // per-pack outputs land at the ray's slot of the full image
+            mask[o] = sm;
+            depth[o] = normalize_depth ? sd / (sm + 1e-10f) : sd;
+            if (rgb) { rgb_out[o * 3] = sr[0]; rgb_out[o * 3 + 1] = sr[1]; rgb_out[o * 3 + 2] = sr[2]; }
+            if (nab) { nab_out[o * 3] = sn[0]; nab_out[o * 3 + 1] = sn[1]; nab_out[o * 3 + 2] = sn[2]; }
         }
     }
 }
@@ -221,16 +222,17 @@ k_composite_bwd(const float *__restrict__ alpha, const float *__restrict__ t, co
                 const float *__restrict__ vw, const int64_t *__restrict__ pi, int64_t n_packs, float eps, float thre, int normalize_depth,
                 const float *__restrict__ mask, const float *__restrict__ depth, const float *__restrict__ g_mask, const float *__restrict__ g_depth,
                 const float *__restrict__ g_rgb, const float *__restrict__ g_nab, const float *__restrict__ g_vw_ext,
-                float *__restrict__ d_alpha, float *__restrict__ d_rgb, float *__restrict__ d_nab) {
+                const int64_t *__restrict__ ray_index, float *__restrict__ d_alpha, float *__restrict__ d_rgb, float *__restrict__ d_nab) {
     const int lane = threadIdx.x & 31;
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
-        const float gm = g_mask ? g_mask[p] : 0.f, gd = g_depth ? g_depth[p] : 0.f;
-        const float M = mask[p], Dp = depth[p];
+        const int64_t o = ray_index ? ray_index[p] : p;
+        const float gm = g_mask ? g_mask[o] : 0.f, gd = g_depth ? g_depth[o] : 0.f;
+        const float M = mask[o], Dp = depth[o];
         const float inv = normalize_depth ? 1.f / (M + 1e-10f) : 1.f;
         float gr[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
-        if (g_rgb) { gr[0] = g_rgb[p * 3]; gr[1] = g_rgb[p * 3 + 1]; gr[2] = g_rgb[p * 3 + 2]; }
-        if (g_nab) { gn[0] = g_nab[p * 3]; gn[1] = g_nab[p * 3 + 1]; gn[2] = g_nab[p * 3 + 2]; }
+        if (g_rgb) { gr[0] = g_rgb[o * 3]; gr[1] = g_rgb[o * 3 + 1]; gr[2] = g_rgb[o * 3 + 2]; }
+        if (g_nab) { gn[0] = g_nab[o * 3]; gn[1] = g_nab[o * 3 + 1]; gn[2] = g_nab[o * 3 + 2]; }
         // pass 1: gw per sample (kept in d_alpha as scratch), accum = sum gw * w
         float accum = 0.f;
         for (int64_t k = lane; k < n; k += 32) {
@@ -297,7 +299,7 @@ extern "C" int nsb_packed_invert_cdf_shared_u(const float *bins, const float *cd
 }
 
 extern "C" int nsb_neus_alpha_forward(const float *sdf, const int64_t *pack_infos, int64_t n_packs, const float *inv_s_dev, float early_stop_eps,
-                                      float alpha_thre, float *alpha, uint8_t *selector, int64_t *num_steps, void *stream) {
+                                      float alpha_thre, float *alpha, uint8_t *selector, int32_t *num_steps, void *stream) {
     if (n_packs == 0) return 0;
     NSB_REQUIRE(sdf && pack_infos && inv_s_dev && alpha && selector && num_steps, "nsb_neus_alpha_forward: NULL argument");
     k_neus_alpha_fwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(sdf, pack_infos, n_packs, inv_s_dev, early_stop_eps, alpha_thre, alpha, selector, num_steps);
@@ -313,24 +315,25 @@ extern "C" int nsb_neus_alpha_backward(const float *sdf, const int64_t *pack_inf
 }
 
 extern "C" int nsb_composite_forward(const float *alpha, const float *t, const float *rgb, const float *nablas, const int64_t *pack_infos,
-                                     int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth, float *vw, float *mask,
-                                     float *depth, float *rgb_out, float *nablas_out, void *stream) {
+                                     int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth, const int64_t *ray_index,
+                                     float *vw, float *mask, float *depth, float *rgb_out, float *nablas_out, void *stream) {
     if (n_packs == 0) return 0;
     NSB_REQUIRE(alpha && t && pack_infos && vw && mask && depth, "nsb_composite_forward: NULL argument");
     NSB_REQUIRE((!rgb || rgb_out) && (!nablas || nablas_out), "nsb_composite_forward: missing output buffer");
     k_composite_fwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(alpha, t, rgb, nablas, pack_infos, n_packs, early_stop_eps, alpha_thre, normalize_depth,
-                                                            vw, mask, depth, rgb_out, nablas_out);
+                                                            ray_index, vw, mask, depth, rgb_out, nablas_out);
     return check_launch("nsb_composite_forward");
 }
 
 extern "C" int nsb_composite_backward(const float *alpha, const float *t, const float *rgb, const float *nablas, const float *vw,
                                       const int64_t *pack_infos, int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth,
                                       const float *mask, const float *depth, const float *g_mask, const float *g_depth, const float *g_rgb,
-                                      const float *g_nablas, const float *g_vw, float *d_alpha, float *d_rgb, float *d_nablas, void *stream) {
+                                      const float *g_nablas, const float *g_vw, const int64_t *ray_index, float *d_alpha, float *d_rgb,
+                                      float *d_nablas, void *stream) {
     if (n_packs == 0) return 0;
     NSB_REQUIRE(alpha && t && vw && pack_infos && mask && depth && d_alpha, "nsb_composite_backward: NULL argument");
     NSB_REQUIRE((!rgb || d_rgb) && (!nablas || d_nablas), "nsb_composite_backward: missing output buffer");
     k_composite_bwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(alpha, t, rgb, nablas, vw, pack_infos, n_packs, early_stop_eps, alpha_thre, normalize_depth,
-                                                            mask, depth, g_mask, g_depth, g_rgb, g_nablas, g_vw, d_alpha, d_rgb, d_nablas);
+                                                            mask, depth, g_mask, g_depth, g_rgb, g_nablas, g_vw, ray_index, d_alpha, d_rgb, d_nablas);
     return check_launch("nsb_composite_backward");
 }

@@ -1,0 +1,345 @@
+// Glue of the per-ray NeuS query for sm_100a: the index bookkeeping between the big kernels (march -> up-sample -> boundary
+// SDF -> alpha -> colour -> composite) that the reference does with ~200 ATen launches and ~20 host syncs per call
+// (graphics/neus/neus_ray_query.py:732-1104, pack_ops.py, occgrid_raymarch.py:60-112) -- here one launch per step:
+//
+//   k_scan_counts        exclusive scan of per-ray counts + compaction of the non-empty rays, one CTA, totals on the device
+//                        (replaces cumsum / nonzero / stack / index chains; the host reads the two totals once)
+//   k_merge_vals         merge_two_packs_sorted_aligned + the scatter of both payloads (depth, sdf) into the merged buffers
+//                        (pack_ops.py:529-560 + neus_ray_query.py:893-905)
+//   k_assemble_boundary  depths_1 = sort(cat(fine stages)); merge_two_batch_a_includes_b with the coarse samples; ridx;
+//                        mid-points  (neus_ray_query.py:907-976)
+//   k_compact_samples    packed_volume_render_compression's gather of the kept samples (pack_ops.py:286-291 + :1010-1030)
+//
+// All outputs are the reference's values (same fp32 roundings; ties between equal depths carry equal payloads, so the order
+// inside a tie is immaterial).
+#include "nsb_common.cuh"
+
+namespace nsb {
+
+__device__ __forceinline__ int64_t gwarp_() { return ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; }
+__device__ __forceinline__ int64_t nwarps_() { return ((int64_t)gridDim.x * blockDim.x) >> 5; }
+
+// ------------------------------------------------------------------------------------------------ scan + compaction
+// counts[N] (int32, >= 0)  ->  first[N] (exclusive prefix sum), and for the non-zero entries, in order:
+// nz_index[j] = i, nz_pack[j] = (first_i, counts_i) (int64), optionally gathered values nz_src[j] = src[i];
+// info2[N,2] = (first_i, counts_i) int32 (the reference's `packed_info`); totals = (sum, number of non-zeros).
+constexpr int kScanT = 1024;
+__global__ void __launch_bounds__(kScanT)
+k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int32_t *__restrict__ first, int32_t *__restrict__ info2,
+              int64_t *__restrict__ nz_index, int64_t *__restrict__ nz_pack, const int64_t *__restrict__ src, int64_t *__restrict__ nz_src,
+              int64_t *__restrict__ totals) {
+    __shared__ int64_t s_sum[32];
+    __shared__ int32_t s_nz[32];
+    __shared__ int64_t carry_sum;
+    __shared__ int32_t carry_nz;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry_sum = 0; carry_nz = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += kScanT) {
+        const int64_t i = base + tid;
+        const int32_t c = i < n ? counts[i] : 0;
+        const int32_t z = c > 0 ? 1 : 0;
+        int64_t ps = c;
+        int32_t pz = z;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t a = __shfl_up_sync(0xffffffffu, ps, o);
+            const int32_t b = __shfl_up_sync(0xffffffffu, pz, o);
+            if (lane >= o) { ps += a; pz += b; }
+        }
+        if (lane == 31) { s_sum[warp] = ps; s_nz[warp] = pz; }
+        __syncthreads();
+        if (warp == 0) {
+            int64_t a = s_sum[lane];
+            int32_t b = s_nz[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t a2 = __shfl_up_sync(0xffffffffu, a, o);
+                const int32_t b2 = __shfl_up_sync(0xffffffffu, b, o);
+                if (lane >= o) { a += a2; b += b2; }
+            }
+            s_sum[lane] = a;
+            s_nz[lane] = b;
+        }
+        __syncthreads();
+        const int64_t excl = carry_sum + (warp ? s_sum[warp - 1] : 0) + ps - c;
+        const int32_t rank = carry_nz + (warp ? s_nz[warp - 1] : 0) + pz - z;
+        if (i < n) {
+            if (first) first[i] = (int32_t)excl;
+            if (info2) { info2[2 * i] = (int32_t)excl; info2[2 * i + 1] = c; }
+            if (z) {
+                if (nz_index) nz_index[rank] = i;
+                if (nz_pack) { nz_pack[2 * rank] = excl; nz_pack[2 * rank + 1] = c; }
+                if (nz_src) nz_src[rank] = src[i];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { carry_sum += s_sum[31]; carry_nz += s_nz[31]; }
+        __syncthreads();
+    }
+    if (tid == 0) { totals[0] = carry_sum; totals[1] = carry_nz; }
+}
+
+// ------------------------------------------------------------------------------------------------ merge with payloads
+// pack p of a: (dep_a, sdf_a)[pi_a[p]] sorted by depth; pack p of b: row p of (dep_b, sdf_b)[P, nb], sorted.
+// merged position of a_i = i + #{b <= a_i}, of b_j = j + #{a < b_j}  (kernel_merge_two_packs_sorted_aligned's rule).
+// pi_m[p] = (pi_a[p].first + p * nb, n_a + nb).  One warp per pack; b lives in shared memory.
+constexpr int kMergeWarps = 8;
+__global__ void __launch_bounds__(kMergeWarps * 32)
+k_merge_vals(const float *__restrict__ dep_a, const float *__restrict__ sdf_a, const int64_t *__restrict__ pi_a, const float *__restrict__ dep_b,
+             const float *__restrict__ sdf_b, int64_t n_packs, int nb, float *__restrict__ dep_m, float *__restrict__ sdf_m,
+             int64_t *__restrict__ pi_m) {
+    extern __shared__ float s_b[];                        // [warps][nb]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float *bb = s_b + w * nb;
+    for (int64_t p = gwarp_(); p < n_packs; p += nwarps_()) {
+        const int64_t a0 = pi_a[2 * p], na = pi_a[2 * p + 1];
+        const int64_t m0 = a0 + p * nb;
+        __syncwarp();
+        for (int j = lane; j < nb; j += 32) bb[j] = dep_b[p * nb + j];
+        __syncwarp();
+        if (lane == 0) { pi_m[2 * p] = m0; pi_m[2 * p + 1] = na + nb; }
+        for (int64_t i = lane; i < na; i += 32) {
+            const float v = dep_a[a0 + i];
+            int lo = 0, cnt = nb;                         // upper bound of v in b
+            while (cnt > 0) {
+                const int step = cnt >> 1;
+                if (bb[lo + step] <= v) { lo += step + 1; cnt -= step + 1; } else cnt = step;
+            }
+            dep_m[m0 + i + lo] = v;
+            if (sdf_m) sdf_m[m0 + i + lo] = sdf_a[a0 + i];
+        }
+        for (int j = lane; j < nb; j += 32) {
+            const float v = bb[j];
+            int64_t lo = 0, cnt = na;                     // lower bound of v in a
+            while (cnt > 0) {
+                const int64_t step = cnt >> 1;
+                if (dep_a[a0 + lo + step] < v) { lo += step + 1; cnt -= step + 1; } else cnt = step;
+            }
+            dep_m[m0 + j + lo] = v;
+            if (sdf_m) sdf_m[m0 + j + lo] = sdf_b[p * nb + j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ boundary samples
+// Ray r of the R tested rays carries nc coarse depths (sorted); if r == ridx_hit[j] it also carries the nf fine depths of
+// row j (a concatenation of sorted runs).  Output pack r = the sorted union; first_r = nc r + nf #{hit rays < r}.
+//   d1[first + k] = k-th smallest;  mid[first + k] = d1_k + (d1_{k+1} - d1_k) / 2 (last: + 0);  ridx_all = r.
+constexpr int kAsmWarps = 8;
+__global__ void __launch_bounds__(kAsmWarps * 32)
+k_assemble_boundary(const float *__restrict__ coarse, int64_t n_rays, int nc, const int64_t *__restrict__ ridx_hit, int64_t n_hit,
+                    const float *__restrict__ fine, int nf, float *__restrict__ d1, float *__restrict__ mid, int64_t *__restrict__ ridx_all,
+                    int64_t *__restrict__ pack_infos) {
+    extern __shared__ float s_v[];                        // [warps][2][nc + nf]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cap = nc + nf;
+    float *raw = s_v + (size_t)w * 2 * cap, *srt = raw + cap;
+    for (int64_t r = gwarp_(); r < n_rays; r += nwarps_()) {
+        int64_t lo = 0, cnt = n_hit;                      // lower bound of r in ridx_hit
+        while (cnt > 0) {
+            const int64_t step = cnt >> 1;
+            if (ridx_hit[lo + step] < r) { lo += step + 1; cnt -= step + 1; } else cnt = step;
+        }
+        const bool hit = lo < n_hit && ridx_hit[lo] == r;
+        const int n = nc + (hit ? nf : 0);
+        const int64_t first = (int64_t)nc * r + (int64_t)nf * lo;
+        __syncwarp();
+        for (int k = lane; k < nc; k += 32) raw[k] = coarse[r * nc + k];
+        if (hit) for (int k = lane; k < nf; k += 32) raw[nc + k] = fine[lo * nf + k];
+        __syncwarp();
+        if (hit) {
+            for (int e = lane; e < n; e += 32) {          // stable rank by counting
+                const float v = raw[e];
+                int rank = 0;
+                for (int k = 0; k < n; ++k) {
+                    const float u = raw[k];
+                    rank += (u < v || (u == v && k < e)) ? 1 : 0;
+                }
+                srt[rank] = v;
+            }
+        } else {
+            for (int e = lane; e < n; e += 32) srt[e] = raw[e];
+        }
+        __syncwarp();
+        if (lane == 0) { pack_infos[2 * r] = first; pack_infos[2 * r + 1] = n; }
+        for (int k = lane; k < n; k += 32) {
+            const float v = srt[k];
+            const float diff = (k < n - 1) ? __fsub_rn(srt[k + 1], v) : 0.f;
+            d1[first + k] = v;
+            mid[first + k] = __fadd_rn(v, __fmul_rn(diff, 0.5f));
+            ridx_all[first + k] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ compaction of the kept samples
+// selector[S] marks the samples packed_volume_render_compression keeps; first_out[p] = exclusive scan of the kept counts.
+// Kept sample s of pack p -> slot first_out[p] + (number of kept samples before s in the pack).
+__global__ void __launch_bounds__(256)
+k_compact_samples(const uint8_t *__restrict__ selector, const int64_t *__restrict__ pi, const int32_t *__restrict__ first_out,
+                  const int32_t *__restrict__ kept, int64_t n_packs, const int64_t *__restrict__ ridx_all, const float *__restrict__ t,
+                  const float *__restrict__ alpha, int64_t *__restrict__ pidx, int64_t *__restrict__ ridx_c, float *__restrict__ t_c,
+                  float *__restrict__ alpha_c) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t p = gwarp_(); p < n_packs; p += nwarps_()) {
+        const int32_t kp = kept[p];
+        if (kp == 0) continue;
+        const int64_t b = pi[2 * p], n = pi[2 * p + 1];
+        int64_t out = first_out[p];
+        int32_t done = 0;
+        for (int64_t k0 = 0; k0 < n && done < kp; k0 += 32) {
+            const int64_t k = k0 + lane;
+            const bool sel = k < n && selector[b + k] != 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, sel);
+            if (sel) {
+                const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+                pidx[o] = b + k;
+                ridx_c[o] = ridx_all[b + k];
+                t_c[o] = t[b + k];
+                alpha_c[o] = alpha[b + k];
+            }
+            const int c = __popc(m);
+            out += c;
+            done += c;
+        }
+    }
+}
+
+// dst[idx[j]] = src[j]  (adjoint of a gather with unique indices; dst is zero-filled by the caller)
+__global__ void __launch_bounds__(256)
+k_scatter_f32(const float *__restrict__ src, const int64_t *__restrict__ idx, int64_t n, float *__restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) dst[idx[j]] = src[j];
+}
+
+
+// ------------------------------------------------------------------------------------------------ AABB ray test
+// AABBSpace.ray_test (models/spatial/aabb.py:71-99) + ray_box_intersection_fast_float_nocheck (graphics/raytest.py:162-167):
+// o' = (o - c) / r, d' = d / r; slab test against [-1,1]^3; clamp by near / far; flag = the reference's mask.
+// torch.minimum / maximum / max(dim) / clamp propagate NaN -- so do these helpers (a NaN interval fails every comparison).
+__device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+
+struct RayTestArgs {
+    float c[3], r[3];
+    float near_clip, far_clip;
+    int has_near, has_far;
+};
+
+__global__ void __launch_bounds__(256)
+k_ray_test_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n, const RayTestArgs a, float *__restrict__ o_n,
+                float *__restrict__ d_n, float *__restrict__ near, float *__restrict__ far, int32_t *__restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float tn = 0.f, tf = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float o = __fdiv_rn(__fsub_rn(rays_o[i * 3 + d], a.c[d]), a.r[d]);
+            const float v = __fdiv_rn(rays_d[i * 3 + d], a.r[d]);
+            o_n[i * 3 + d] = o;
+            d_n[i * 3 + d] = v;
+            const float ta = __fdiv_rn(__fsub_rn(-1.f, o), v), tb = __fdiv_rn(__fsub_rn(1.f, o), v);
+            const float lo = min_nan(ta, tb), hi = max_nan(ta, tb);
+            tn = d == 0 ? lo : max_nan(tn, lo);
+            tf = d == 0 ? hi : min_nan(tf, hi);
+        }
+        if (a.has_near && tn == tn) tn = fmaxf(tn, a.near_clip);      // clamp_min_ keeps NaN
+        if (a.has_far && tf == tf) tf = fminf(tf, a.far_clip);
+        bool m = (tf > tn) && (tf > (a.has_near ? a.near_clip : 0.f));
+        if (a.has_far) m = m && (tn < a.far_clip);
+        near[i] = tn;
+        far[i] = tf;
+        flag[i] = m ? 1 : 0;
+    }
+}
+
+// compaction of the rays that passed: row j of every output = row idx[j] of the inputs
+__global__ void __launch_bounds__(256)
+k_gather_rays(const int64_t *__restrict__ idx, int64_t n, const float *__restrict__ o_n, const float *__restrict__ d_n, const float *__restrict__ near,
+              const float *__restrict__ far, float *__restrict__ o_c, float *__restrict__ d_c, float *__restrict__ near_c, float *__restrict__ far_c) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int64_t i = idx[j];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { o_c[j * 3 + d] = o_n[i * 3 + d]; d_c[j * 3 + d] = d_n[i * 3 + d]; }
+        near_c[j] = near[i];
+        far_c[j] = far[i];
+    }
+}
+
+}  // namespace nsb
+
+using namespace nsb;
+#define STREAM ((cudaStream_t)stream)
+
+extern "C" int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first, int32_t *info2, int64_t *nz_index, int64_t *nz_pack,
+                               const int64_t *src, int64_t *nz_src, int64_t *totals, void *stream) {
+    NSB_REQUIRE(totals, "nsb_scan_counts: totals is NULL");
+    NSB_REQUIRE(n == 0 || counts, "nsb_scan_counts: counts is NULL");
+    NSB_REQUIRE(!nz_src || src, "nsb_scan_counts: nz_src needs src");
+    k_scan_counts<<<1, kScanT, 0, STREAM>>>(counts, n, first, info2, nz_index, nz_pack, src, nz_src, totals);
+    return check_launch("nsb_scan_counts");
+}
+
+extern "C" int nsb_merge_sorted_vals(const float *dep_a, const float *sdf_a, const int64_t *pack_infos_a, const float *dep_b, const float *sdf_b,
+                                     int64_t n_packs, int32_t n_b, float *dep_m, float *sdf_m, int64_t *pack_infos_m, void *stream) {
+    if (n_packs == 0) return 0;
+    NSB_REQUIRE(dep_a && pack_infos_a && dep_b && dep_m && pack_infos_m, "nsb_merge_sorted_vals: NULL argument");
+    NSB_REQUIRE((sdf_m == nullptr) || (sdf_a && sdf_b), "nsb_merge_sorted_vals: sdf_m needs sdf_a and sdf_b");
+    NSB_REQUIRE(n_b > 0 && n_b <= 1024, "nsb_merge_sorted_vals: n_b must be in [1, 1024]");
+    const size_t smem = (size_t)kMergeWarps * n_b * sizeof(float);
+    k_merge_vals<<<wave_grid(n_packs * 32, kMergeWarps * 32, 8), kMergeWarps * 32, smem, STREAM>>>(dep_a, sdf_a, pack_infos_a, dep_b, sdf_b, n_packs, n_b,
+                                                                                                 dep_m, sdf_m, pack_infos_m);
+    return check_launch("nsb_merge_sorted_vals");
+}
+
+extern "C" int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_t n_coarse, const int64_t *ridx_hit, int64_t n_hit, const float *fine,
+                                     int32_t n_fine, float *d1, float *mid, int64_t *ridx_all, int64_t *pack_infos, void *stream) {
+    if (n_rays == 0) return 0;
+    NSB_REQUIRE(coarse && d1 && mid && ridx_all && pack_infos, "nsb_assemble_boundary: NULL argument");
+    NSB_REQUIRE(n_hit == 0 || (ridx_hit && fine), "nsb_assemble_boundary: hit rays need ridx_hit and fine");
+    NSB_REQUIRE(n_coarse > 0 && n_fine >= 0 && n_coarse + n_fine <= 1024, "nsb_assemble_boundary: n_coarse + n_fine must be <= 1024");
+    const size_t smem = (size_t)kAsmWarps * 2 * (n_coarse + n_fine) * sizeof(float);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_assemble_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    NSB_REQUIRE(smem <= 96 * 1024, "nsb_assemble_boundary: too many samples per ray for shared memory");
+    k_assemble_boundary<<<wave_grid(n_rays * 32, kAsmWarps * 32, 8), kAsmWarps * 32, smem, STREAM>>>(coarse, n_rays, n_coarse, ridx_hit, n_hit, fine, n_fine,
+                                                                                                  d1, mid, ridx_all, pack_infos);
+    return check_launch("nsb_assemble_boundary");
+}
+
+extern "C" int nsb_compact_samples(const uint8_t *selector, const int64_t *pack_infos, const int32_t *first_out, const int32_t *kept, int64_t n_packs,
+                                   const int64_t *ridx_all, const float *t, const float *alpha, int64_t *pidx, int64_t *ridx_c, float *t_c,
+                                   float *alpha_c, void *stream) {
+    if (n_packs == 0) return 0;
+    NSB_REQUIRE(selector && pack_infos && first_out && kept && ridx_all && t && alpha && pidx && ridx_c && t_c && alpha_c,
+                "nsb_compact_samples: NULL argument");
+    k_compact_samples<<<wave_grid(n_packs * 32, 256, 8), 256, 0, STREAM>>>(selector, pack_infos, first_out, kept, n_packs, ridx_all, t, alpha, pidx, ridx_c,
+                                                                          t_c, alpha_c);
+    return check_launch("nsb_compact_samples");
+}
+
+extern "C" int nsb_scatter_f32(const float *src, const int64_t *idx, int64_t n, float *dst, void *stream) {
+    if (n == 0) return 0;
+    NSB_REQUIRE(src && idx && dst, "nsb_scatter_f32: NULL argument");
+    k_scatter_f32<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(src, idx, n, dst);
+    return check_launch("nsb_scatter_f32");
+}
+
+extern "C" int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64_t n, const float *center3, const float *radius3, int has_near,
+                                 float near_clip, int has_far, float far_clip, float *o_n, float *d_n, float *near, float *far, int32_t *flag,
+                                 void *stream) {
+    if (n == 0) return 0;
+    NSB_REQUIRE(rays_o && rays_d && center3 && radius3 && o_n && d_n && near && far && flag, "nsb_ray_test_aabb: NULL argument");
+    RayTestArgs a{{center3[0], center3[1], center3[2]}, {radius3[0], radius3[1], radius3[2]}, near_clip, far_clip, has_near, has_far};
+    k_ray_test_aabb<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(rays_o, rays_d, n, a, o_n, d_n, near, far, flag);
+    return check_launch("nsb_ray_test_aabb");
+}
+
+extern "C" int nsb_gather_rays(const int64_t *idx, int64_t n, const float *o_n, const float *d_n, const float *near, const float *far, float *o_c,
+                               float *d_c, float *near_c, float *far_c, void *stream) {
+    if (n == 0) return 0;
+    NSB_REQUIRE(idx && o_n && d_n && near && far && o_c && d_c && near_c && far_c, "nsb_gather_rays: NULL argument");
+    k_gather_rays<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(idx, n, o_n, d_n, near, far, o_c, d_c, near_c, far_c);
+    return check_launch("nsb_gather_rays");
+}

@@ -163,11 +163,11 @@ class LoTDNeuSModel(LoTDNeuS):
 
     def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d):
         ret = super().forward_sdf_on_rays(ridx, t, rays_o, rays_d)
-        if self.training and self.accel is not None and self.accel.occ.should_collect_samples and not torch.is_grad_enabled():
+        if self.training and self.accel is not None and self.accel.occ.should_collect_samples:
             # the fused query never materialised the points; rebuild them only to feed the accel's statistics
             r = ridx.unsqueeze(-1).expand(t.shape) if t.dim() == 2 else ridx
             x = torch.addcmul(rays_o[r], rays_d[r], t.unsqueeze(-1))
-            self.accel.collect_samples(x, val=ret["sdf"])
+            self.accel.collect_samples(x, val=ret["sdf"].detach())
         return ret
 
     def forward_sdf_nablas(self, x, skip_accel=False, **kw):
@@ -230,11 +230,11 @@ class LoTDNeuSModel(LoTDNeuS):
             details.update(qd)
         if render_per_obj_individual and volume_buffer["type"] != "empty":
             volume_integration(volume_buffer, rendered, training=self.training,
-                               depth_use_normalized_vw=config.get("depth_use_normalized_vw", True), nablas_key="nablas")
+                               depth_use_normalized_vw=config.get("depth_use_normalized_vw", True), nablas_key="nablas", fresh=True)
         return raw
 
 
-def volume_integration(volume_buffer, rendered, training=True, depth_use_normalized_vw=True, nablas_key="nablas"):
+def volume_integration(volume_buffer, rendered, training=True, depth_use_normalized_vw=True, nablas_key="nablas", fresh=False):
     """vw = alpha_to_vw(alpha); mask = sum vw; depth = sum vw/(mask+1e-10) t; rgb = sum vw rgb; normals = sum vw nablas
     (single_volume_renderer.py:73-102 / renderer_mixin.py:396-439).  Writes into `rendered` at rays_inds_hit."""
     hit = volume_buffer["rays_inds_hit"]
@@ -244,6 +244,18 @@ def volume_integration(volume_buffer, rendered, training=True, depth_use_normali
         if nab is not None and not training:
             nab = F.normalize(nab.clamp(-1, 1), dim=-1)
         rgb = volume_buffer.get("rgb") if "rgb_volume" in rendered else None
+        if fresh and rendered["mask_volume"].dim() == 1:
+            # `rendered` holds nothing yet (all zeros): the kernel writes whole-image buffers at rays_inds_hit directly
+            vw, m, d, c, nn_ = neus_fused.composite(volume_buffer["opacity_alpha"], volume_buffer["t"], volume_buffer["pack_infos_hit"], rgb=rgb,
+                                                     nablas=nab, normalize_depth=depth_use_normalized_vw, ray_index=hit,
+                                                     n_rays=rendered["mask_volume"].shape[0])
+            volume_buffer["vw"] = vw
+            rendered["mask_volume"], rendered["depth_volume"] = m, d
+            if c is not None:
+                rendered["rgb_volume"] = c
+            if nn_ is not None:
+                rendered["normals_volume"] = nn_
+            return rendered
         vw, m, d, c, nn_ = neus_fused.composite(volume_buffer["opacity_alpha"], volume_buffer["t"], volume_buffer["pack_infos_hit"],
                                                  rgb=rgb, nablas=nab, normalize_depth=depth_use_normalized_vw)
         volume_buffer["vw"] = vw

@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 
 from ..graphics.raytest import ray_box_intersection_fast_float_nocheck
+from .. import _lib as L
 
 
 class AABBSpace(nn.Module):
@@ -40,6 +41,9 @@ class AABBSpace(nn.Module):
 
     def ray_test(self, rays_o, rays_d, near=None, far=None, return_rays=True, normalized=False, **extra_ray_data):
         """Slab test against the unit cube -> dict(num_rays, rays_inds, near, far, rays_o, rays_d, **extras) of the hit rays."""
+        if (rays_o.is_cuda and rays_o.dim() == 2 and rays_o.dtype == torch.float32 and rays_d.dtype == torch.float32 and return_rays
+                and not rays_o.requires_grad and not rays_d.requires_grad and not isinstance(near, torch.Tensor) and not isinstance(far, torch.Tensor)):
+            return self._ray_test_fused(rays_o, rays_d, near, far, normalized, extra_ray_data)
         if not normalized:
             rays_o, rays_d = self.normalize_rays(rays_o, rays_d)
         with torch.no_grad():
@@ -56,4 +60,34 @@ class AABBSpace(nn.Module):
         ret.update({k: (v[ridx] if isinstance(v, torch.Tensor) else v) for k, v in extra_ray_data.items()})
         if return_rays:
             ret.update(rays_o=rays_o[ridx], rays_d=rays_d[ridx])
+        return ret
+
+    @torch.no_grad()
+    def _ray_test_fused(self, rays_o, rays_d, near, far, normalized, extra_ray_data):
+        """The same test as below in three launches and one host read (csrc/neus_glue.cu: k_ray_test_aabb, k_scan_counts, k_gather_rays)."""
+        from ..graphics.neus_fused import scan_counts
+        import ctypes
+        R, dev = rays_o.shape[0], rays_o.device
+        if getattr(self, "_host_cr", None) is None or self._host_cr[0] != (self.aabb.data_ptr(), self.aabb._version):
+            c, r = self.center.tolist(), self.radius3d.tolist()
+            self._host_cr = ((self.aabb.data_ptr(), self.aabb._version), (ctypes.c_float * 3)(*c), (ctypes.c_float * 3)(*r))
+        c3, r3 = self._host_cr[1], self._host_cr[2]
+        if normalized:
+            c3, r3 = (ctypes.c_float * 3)(0., 0., 0.), (ctypes.c_float * 3)(1., 1., 1.)
+        o_n, d_n = torch.empty(R, 3, device=dev), torch.empty(R, 3, device=dev)
+        nr, fr = torch.empty(R, device=dev), torch.empty(R, device=dev)
+        flag = torch.empty(R, dtype=torch.int32, device=dev)
+        L.check(L.lib().nsb_ray_test_aabb(L.ptr(rays_o.contiguous(), "f32"), L.ptr(rays_d.contiguous(), "f32"), L.c_i64(R), c3, r3,
+                                          ctypes.c_int(0 if near is None else 1), L.c_f32(0. if near is None else near),
+                                          ctypes.c_int(0 if far is None else 1), L.c_f32(0. if far is None else far), L.ptr(o_n), L.ptr(d_n),
+                                          L.ptr(nr), L.ptr(fr), L.ptr(flag), L.stream_ptr()), "ray_test_aabb")
+        sc = scan_counts(flag, want_index=True)
+        n, ridx = sc["n_nonzero"], sc["index"]
+        o_c, d_c = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+        n_c, f_c = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        L.check(L.lib().nsb_gather_rays(L.ptr(ridx, "i64"), L.c_i64(n), L.ptr(o_n), L.ptr(d_n), L.ptr(nr), L.ptr(fr), L.ptr(o_c), L.ptr(d_c),
+                                        L.ptr(n_c), L.ptr(f_c), L.stream_ptr()), "gather_rays")
+        ret = dict(num_rays=n, rays_inds=ridx, near=n_c, far=f_c)
+        ret.update({k: (v[ridx] if isinstance(v, torch.Tensor) else v) for k, v in extra_ray_data.items()})
+        ret.update(rays_o=o_c, rays_d=d_c)
         return ret

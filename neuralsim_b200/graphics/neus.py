@@ -91,6 +91,51 @@ def neus_ray_sdf_to_upsample_alpha(sdf, depth_samples, inv_s):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, with_rgb, with_normal, nablas_has_grad, forward_inv_s, num_coarse, march_cfg, num_fine,
+                 upsample_inv_s, factors, use_estimate_alpha):
+    """The query below with every stage between the big kernels as ONE launch (csrc/neus_glue.cu, csrc/neus_fused.cu) and three host
+    reads in total (march size, compression size, + the ray test's): same samples, same values as the chain it replaces -- the chain
+    stays in this file as the specification (tests/test_neus_fused_gpu.py runs both).  None -> no ray marched into an occupied voxel
+    (the caller falls back to the general path for that rare case)."""
+    rays_o, rays_d, near, far, rays_inds = itemgetter("rays_o", "rays_d", "near", "far", "rays_inds")(ray_tested)
+    dtype, n_stage = rays_o.dtype, len(factors)
+    mc = dict(march_cfg)
+    fac = mc.pop("step_size_factor", 1.0)
+    mc["step_size"] = mc.get("step_size", 1e-3) * fac
+    mc["dt_gamma"] = mc.get("dt_gamma", 0.0) * fac
+    mc.setdefault("max_steps", 512)
+    rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
+    depths_coarse_1 = batch_sample_step_linear(near, far, num_coarse + 1, prefix_shape=[rays_o.shape[0]])
+    marched = neus_fused.march_lean(model.accel.occ.occ_grid, rays_o, rays_d, near.contiguous(), far.contiguous(), **mc)
+    if marched is None:
+        return None
+    ridx_hit, pinfo_march, depth_samples, ridx = marched
+    pack_infos = pinfo_march
+    with torch.no_grad():
+        sdf = model.forward_sdf_on_rays(ridx, depth_samples, rays_o, rays_d)["sdf"].to(dtype)
+        fine_stages = []
+        for i, factor in enumerate(factors):
+            cdf = neus_fused.upsample_cdf(sdf, depth_samples, pack_infos, upsample_inv_s * factor, use_estimate_alpha)
+            fine = neus_fused.sample_cdf_uniform(depth_samples, cdf, pack_infos, num_fine[i])
+            fine_stages.append(fine)
+            if i < n_stage - 1:         # (the reference also merges after the last stage; nothing reads that result)
+                sdf_fine = model.forward_sdf_on_rays(ridx_hit, fine, rays_o, rays_d)["sdf"].to(dtype).contiguous()
+                depth_samples, sdf, pack_infos = neus_fused.merge_sorted_vals(depth_samples, sdf, pack_infos, fine, sdf_fine)
+        fine_all = torch.cat(fine_stages, dim=-1) if n_stage > 1 else fine_stages[0]
+        d1, mid, ridx_all, pinfo = neus_fused.assemble_boundary(depths_coarse_1.contiguous(), ridx_hit, fine_all.contiguous())
+    sdf_b = model.forward_sdf_on_rays(ridx_all, d1, rays_o, rays_d)["sdf"].to(dtype)
+    comp = neus_fused.neus_alpha_compact(sdf_b, forward_inv_s, pinfo, ridx_all, mid, rays_inds)
+    if comp is None:
+        return dict(type="empty", rays_inds_hit=[]), {}
+    volume_buffer = dict(type="packed", rays_inds_hit=comp["rays_inds_hit"], pack_infos_hit=comp["pack_infos"], t=comp["t"].to(dtype),
+                         opacity_alpha=comp["alpha"].to(dtype))
+    if with_rgb or with_normal:
+        _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, comp["ridx"], comp["t"], nablas_has_grad=nablas_has_grad,
+                          with_rgb=with_rgb, with_normal=with_normal, dtype=dtype)
+    details = {"march.num_per_ray": pinfo_march[:, 1], "render.num_per_ray0": pinfo[:, 1], "render.num_per_ray": comp["pack_infos"][:, 1]}
+    return volume_buffer, details
+
+
 def _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths, *, nablas_has_grad,
                       with_rgb, with_normal, dtype):
     if (FUSED_STAGES and with_rgb and view_dirs is not None and getattr(model, "_color_fusable", lambda: False)()
@@ -142,6 +187,16 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
     R = rays_o.shape[0]
     dir_scale = rays_d.detach().norm(dim=-1)
     view_dirs = rays_d / dir_scale.clamp_min(1.0e-10).unsqueeze(-1) if use_view_dirs else None
+
+    if (FUSED_STAGES and not perturb and num_coarse > 0 and rays_o.is_cuda and dtype == torch.float32 and hasattr(model, "forward_sdf_on_rays")
+            and getattr(getattr(model.accel, "occ", None), "occ_grid", None) is not None and model.accel.occ.occ_grid.dim() == 3
+            and not (rays_o.requires_grad or rays_d.requires_grad or near.requires_grad or far.requires_grad)
+            and set(march_cfg) <= {"step_size", "max_steps", "max_step_size", "dt_gamma", "step_size_factor"}):
+        ret = _query_fused(model, ray_tested, view_dirs, rays_h_appear, with_rgb=with_rgb, with_normal=with_normal, nablas_has_grad=nablas_has_grad,
+                           forward_inv_s=forward_inv_s, num_coarse=num_coarse, march_cfg=march_cfg, num_fine=num_fine, upsample_inv_s=upsample_inv_s,
+                           factors=upsample_inv_s_factors, use_estimate_alpha=upsample_use_estimate_alpha)
+        if ret is not None:
+            return ret
 
     if num_coarse > 0:
         depths_coarse_1, deltas_coarse_1 = batch_sample_step_linear(near, far, num_coarse + 1, perturb=perturb, return_dt=True)

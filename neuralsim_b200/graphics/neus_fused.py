@@ -16,7 +16,8 @@ import torch
 
 from .. import _lib as L
 
-__all__ = ["upsample_cdf", "sample_cdf_uniform", "neus_alpha_compress", "composite"]
+__all__ = ["upsample_cdf", "sample_cdf_uniform", "neus_alpha_compress", "neus_alpha_compact", "composite", "scan_counts", "merge_sorted_vals",
+           "assemble_boundary", "march_lean"]
 
 _U_CACHE = {}
 
@@ -56,7 +57,7 @@ class _NeusAlpha(torch.autograd.Function):
         P = pack_infos.shape[0]
         alpha = torch.empty_like(sdf_c)
         sel = torch.empty(sdf_c.shape[0], dtype=torch.bool, device=sdf_c.device)
-        steps = torch.empty(P, dtype=torch.int64, device=sdf_c.device)
+        steps = torch.empty(P, dtype=torch.int32, device=sdf_c.device)
         L.check(L.lib().nsb_neus_alpha_forward(L.ptr(sdf_c, "f32"), L.ptr(pack_infos, "i64"), L.c_i64(P), L.ptr(inv_c, "f32"),
                                                L.c_f32(early_stop_eps), L.c_f32(alpha_thre), L.ptr(alpha), L.ptr(sel), L.ptr(steps),
                                                L.stream_ptr()), "neus_alpha_forward")
@@ -85,28 +86,151 @@ def neus_alpha_compress(sdf, inv_s, pack_infos, early_stop_eps=1e-4, alpha_thre=
     alpha, sel, steps = _NeusAlpha.apply(sdf, inv_s, pack_infos, early_stop_eps, alpha_thre)
     pidx = sel.nonzero()[..., 0]
     nidx = (steps > 0).nonzero()[..., 0]
-    kept = steps[nidx]
+    kept = steps[nidx].long()
     cs = kept.cumsum(0)
     return alpha, nidx, torch.stack([cs - kept, kept], 1), pidx
 
 
+class _GatherUnique(torch.autograd.Function):
+    """out = the kernel-made gather `src[pidx]` (pidx unique); backward scatters into zeros with one launch."""
+
+    @staticmethod
+    def forward(ctx, src, pidx, gathered):
+        ctx.save_for_backward(pidx)
+        ctx.n = src.shape[0]
+        return gathered
+
+    @staticmethod
+    def backward(ctx, g):
+        pidx, = ctx.saved_tensors
+        g = g.contiguous().float()
+        d = torch.zeros(ctx.n, dtype=torch.float32, device=g.device)
+        L.check(L.lib().nsb_scatter_f32(L.ptr(g, "f32"), L.ptr(pidx, "i64"), L.c_i64(pidx.shape[0]), L.ptr(d), L.stream_ptr()), "scatter_f32")
+        return d, None, None
+
+
+@torch.no_grad()
+def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False, want_pack=False, src=None):
+    """One launch + ONE host read: exclusive scan of int32 counts and compaction of the non-zero entries.
+    -> dict(total, n_nonzero, first?, info2?, index?, pack?, src?) with the compacted outputs already sliced."""
+    n, dev = counts.shape[0], counts.device
+    first = torch.empty(n, dtype=torch.int32, device=dev) if want_first else None
+    info2 = torch.empty(n, 2, dtype=torch.int32, device=dev) if want_info2 else None
+    index = torch.empty(n, dtype=torch.int64, device=dev) if want_index else None
+    pack = torch.empty(n, 2, dtype=torch.int64, device=dev) if want_pack else None
+    nz_src = torch.empty(n, dtype=torch.int64, device=dev) if src is not None else None
+    totals = torch.empty(2, dtype=torch.int64, device=dev)
+    L.check(L.lib().nsb_scan_counts(L.ptr(counts, "i32"), L.c_i64(n), L.ptr(first, allow_none=True), L.ptr(info2, allow_none=True),
+                                    L.ptr(index, allow_none=True), L.ptr(pack, allow_none=True), L.ptr(src, "i64", allow_none=True),
+                                    L.ptr(nz_src, allow_none=True), L.ptr(totals), L.stream_ptr()), "scan_counts")
+    total, nnz = totals.tolist()                      # the one host sync: output sizes are data dependent
+    out = dict(total=int(total), n_nonzero=int(nnz), first=first, info2=info2)
+    out["index"] = index[:nnz] if index is not None else None
+    out["pack"] = pack[:nnz] if pack is not None else None
+    out["src"] = nz_src[:nnz] if nz_src is not None else None
+    return out
+
+
+@torch.no_grad()
+def merge_sorted_vals(dep_a, sdf_a, pack_infos_a, dep_b, sdf_b):
+    """(dep_a, sdf_a) packs + rows of (dep_b, sdf_b)[P, nb] -> merged (dep, sdf | None, pack_infos); both sides sorted."""
+    P, nb = dep_b.shape
+    n = dep_a.shape[0] + P * nb
+    dep_m = torch.empty(n, dtype=torch.float32, device=dep_a.device)
+    sdf_m = torch.empty_like(dep_m) if sdf_a is not None else None
+    pim = torch.empty_like(pack_infos_a)
+    L.check(L.lib().nsb_merge_sorted_vals(L.ptr(dep_a, "f32"), L.ptr(sdf_a, "f32", allow_none=True), L.ptr(pack_infos_a, "i64"), L.ptr(dep_b, "f32"),
+                                          L.ptr(sdf_b, "f32", allow_none=True), L.c_i64(P), L.c_i32(nb), L.ptr(dep_m), L.ptr(sdf_m, allow_none=True),
+                                          L.ptr(pim), L.stream_ptr()), "merge_sorted_vals")
+    return dep_m, sdf_m, pim
+
+
+@torch.no_grad()
+def assemble_boundary(coarse, ridx_hit, fine):
+    """coarse [R, nc] (sorted rows), fine [n_hit, nf] rows of rays ridx_hit -> (d1 [S], mid [S], ridx_all [S], pack_infos [R,2])."""
+    R, nc = coarse.shape
+    n_hit, nf = (fine.shape if fine is not None else (0, 0))
+    S, dev = R * nc + n_hit * nf, coarse.device
+    d1, mid = torch.empty(S, dtype=torch.float32, device=dev), torch.empty(S, dtype=torch.float32, device=dev)
+    ridx_all = torch.empty(S, dtype=torch.int64, device=dev)
+    pi = torch.empty(R, 2, dtype=torch.int64, device=dev)
+    L.check(L.lib().nsb_assemble_boundary(L.ptr(coarse, "f32"), L.c_i64(R), L.c_i32(nc), L.ptr(ridx_hit, "i64", allow_none=True), L.c_i64(n_hit),
+                                          L.ptr(fine, "f32", allow_none=True), L.c_i32(nf), L.ptr(d1), L.ptr(mid), L.ptr(ridx_all), L.ptr(pi),
+                                          L.stream_ptr()), "assemble_boundary")
+    return d1, mid, ridx_all, pi
+
+
+def neus_alpha_compact(sdf, inv_s, pack_infos, ridx_all, t_mid, rays_inds, early_stop_eps=1e-4, alpha_thre=0.0):
+    """neus_packed_sdf_to_alpha + packed_volume_render_compression + the gathers of the kept samples, 4 launches, 1 host read.
+    -> None if nothing is kept, else dict(alpha [K] (differentiable wrt sdf, inv_s), ridx [K], t [K], pack_infos [Pu,2],
+    nidx [Pu], rays_inds_hit [Pu], pidx [K])."""
+    if not isinstance(inv_s, torch.Tensor):
+        inv_s = torch.tensor(float(inv_s), device=sdf.device)
+    alpha, sel, steps = _NeusAlpha.apply(sdf, inv_s, pack_infos, early_stop_eps, alpha_thre)
+    with torch.no_grad():
+        sc = scan_counts(steps, want_first=True, want_index=True, want_pack=True, src=rays_inds)
+        K = sc["total"]
+        if K == 0:
+            return None
+        dev = sdf.device
+        pidx, ridx_c = torch.empty(K, dtype=torch.int64, device=dev), torch.empty(K, dtype=torch.int64, device=dev)
+        t_c, alpha_c = torch.empty(K, dtype=torch.float32, device=dev), torch.empty(K, dtype=torch.float32, device=dev)
+        L.check(L.lib().nsb_compact_samples(L.ptr(sel.view(torch.uint8), "u8"), L.ptr(pack_infos, "i64"), L.ptr(sc["first"], "i32"), L.ptr(steps, "i32"),
+                                            L.c_i64(pack_infos.shape[0]), L.ptr(ridx_all, "i64"), L.ptr(t_mid, "f32"), L.ptr(alpha.detach(), "f32"),
+                                            L.ptr(pidx), L.ptr(ridx_c), L.ptr(t_c), L.ptr(alpha_c), L.stream_ptr()), "compact_samples")
+    alpha_k = _GatherUnique.apply(alpha, pidx, alpha_c) if alpha.requires_grad else alpha_c
+    return dict(alpha=alpha_k, ridx=ridx_c, t=t_c, pack_infos=sc["pack"], nidx=sc["index"], rays_inds_hit=sc["src"], pidx=pidx)
+
+
+@torch.no_grad()
+def march_lean(occ_grid, rays_o, rays_d, near, far, *, step_size, max_steps, max_step_size=1e10, dt_gamma=0.0, roi=None):
+    """occgrid_raymarch (graphics/raymarch.py) reduced to what the NeuS query consumes, without the per-sample temporaries:
+    -> None if no ray hits an occupied voxel, else (ridx_hit [n_hit] i64, pack_infos [n_hit,2] i64, t_starts [M] f32, ridx [M] i64)."""
+    R, dev = rays_o.shape[0], rays_o.device
+    if roi is None:
+        roi = torch.tensor([-1, -1, -1, 1, 1, 1], dtype=torch.float32, device=dev)
+    g = occ_grid.contiguous().view(torch.uint8)
+    res = occ_grid.shape[-3:]
+    args = (L.c_i64(R), L.ptr(rays_o, "f32", "rays_o"), L.ptr(rays_d, "f32", "rays_d"), L.ptr(near, "f32", "near"), L.ptr(far, "f32", "far"),
+            L.ptr(roi, "f32", "roi"), None, L.c_i32(res[0]), L.c_i32(res[1]), L.c_i32(res[2]), L.ptr(g, "u8"), L.c_f32(step_size),
+            L.c_f32(max_step_size), L.c_f32(dt_gamma), ctypes.c_uint32(int(max_steps)))
+    num_steps = torch.empty(R, dtype=torch.int32, device=dev)
+    with L.KERNEL_TIMER.time("march", R):
+        L.check(L.lib().nsb_ray_marching(*args, None, L.ptr(num_steps), None, None, None, None, None, L.stream_ptr()), "ray_marching")
+    sc = scan_counts(num_steps, want_info2=True, want_index=True, want_pack=True)
+    M = sc["total"]
+    if M == 0:
+        return None
+    t_starts = torch.empty(M, dtype=torch.float32, device=dev)
+    ridx = torch.empty(M, dtype=torch.int32, device=dev)
+    with L.KERNEL_TIMER.time("march", R):
+        L.check(L.lib().nsb_ray_marching(*args, L.ptr(sc["info2"]), None, L.ptr(t_starts), None, L.ptr(ridx), None, None, L.stream_ptr()), "ray_marching")
+    return sc["index"], sc["pack"], t_starts, ridx.long()
+
+
 class _Composite(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, alpha, t, rgb, nablas, pack_infos, normalize_depth, early_stop_eps, alpha_thre):
+    def forward(ctx, alpha, t, rgb, nablas, pack_infos, normalize_depth, early_stop_eps, alpha_thre, ray_index, n_rays):
         a, tt = _f32c(alpha), _f32c(t)
         r = None if rgb is None else _f32c(rgb)
         nb = None if nablas is None else _f32c(nablas)
         P, dev = pack_infos.shape[0], a.device
         vw = torch.empty_like(a)
-        mask, depth = torch.empty(P, device=dev), torch.empty(P, device=dev)
-        rgb_o = torch.empty(P, 3, device=dev) if r is not None else None
-        nab_o = torch.empty(P, 3, device=dev) if nb is not None else None
+        if ray_index is None:
+            new = lambda *shape: torch.empty(*shape, device=dev)
+            n_out = P
+        else:                                       # outputs are whole-image buffers; rays without a pack stay 0
+            new = lambda *shape: torch.zeros(*shape, device=dev)
+            n_out = int(n_rays)
+        mask, depth = new(n_out), new(n_out)
+        rgb_o = new(n_out, 3) if r is not None else None
+        nab_o = new(n_out, 3) if nb is not None else None
         L.check(L.lib().nsb_composite_forward(L.ptr(a, "f32"), L.ptr(tt, "f32"), L.ptr(r, "f32", allow_none=True),
                                               L.ptr(nb, "f32", allow_none=True), L.ptr(pack_infos, "i64"), L.c_i64(P), L.c_f32(early_stop_eps),
-                                              L.c_f32(alpha_thre), ctypes.c_int(1 if normalize_depth else 0), L.ptr(vw), L.ptr(mask),
-                                              L.ptr(depth), L.ptr(rgb_o, allow_none=True), L.ptr(nab_o, allow_none=True), L.stream_ptr()),
-                "composite_forward")
-        ctx.save_for_backward(a, tt, r, nb, vw, pack_infos, mask, depth)
+                                              L.c_f32(alpha_thre), ctypes.c_int(1 if normalize_depth else 0), L.ptr(ray_index, "i64", allow_none=True),
+                                              L.ptr(vw), L.ptr(mask), L.ptr(depth), L.ptr(rgb_o, allow_none=True), L.ptr(nab_o, allow_none=True),
+                                              L.stream_ptr()), "composite_forward")
+        ctx.save_for_backward(a, tt, r, nb, vw, pack_infos, mask, depth, ray_index)
         ctx.cfg = (normalize_depth, early_stop_eps, alpha_thre)
         ctx.set_materialize_grads(False)
         empty = a.new_empty(0)
@@ -114,7 +238,7 @@ class _Composite(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_vw, g_mask, g_depth, g_rgb, g_nab):
-        a, tt, r, nb, vw, pack_infos, mask, depth = ctx.saved_tensors
+        a, tt, r, nb, vw, pack_infos, mask, depth, ray_index = ctx.saved_tensors
         normalize_depth, eps, thre = ctx.cfg
         P = pack_infos.shape[0]
 
@@ -129,12 +253,15 @@ class _Composite(torch.autograd.Function):
         L.check(L.lib().nsb_composite_backward(
             P_(a, "f32"), P_(tt, "f32"), P_(r, allow_none=True), P_(nb, allow_none=True), P_(vw, "f32"), P_(pack_infos, "i64"), L.c_i64(P),
             L.c_f32(eps), L.c_f32(thre), ctypes.c_int(1 if normalize_depth else 0), P_(mask), P_(depth), P_(g_mask, allow_none=True),
-            P_(g_depth, allow_none=True), P_(g_rgb, allow_none=True), P_(g_nab, allow_none=True), P_(g_vw, allow_none=True), P_(d_alpha),
-            P_(d_rgb, allow_none=True), P_(d_nab, allow_none=True), L.stream_ptr()), "composite_backward")
-        return d_alpha, None, d_rgb, d_nab, None, None, None, None
+            P_(g_depth, allow_none=True), P_(g_rgb, allow_none=True), P_(g_nab, allow_none=True), P_(g_vw, allow_none=True),
+            P_(ray_index, "i64", allow_none=True), P_(d_alpha), P_(d_rgb, allow_none=True), P_(d_nab, allow_none=True), L.stream_ptr()), "composite_backward")
+        return d_alpha, None, d_rgb, d_nab, None, None, None, None, None, None
 
 
-def composite(alpha, t, pack_infos, rgb=None, nablas=None, normalize_depth=True, early_stop_eps=1e-4, alpha_thre=0.0):
-    """-> (vw [K], mask [P], depth [P], rgb [P,3] | None, normals [P,3] | None); differentiable wrt alpha, rgb, nablas."""
-    vw, mask, depth, rgb_o, nab_o = _Composite.apply(alpha, t, rgb, nablas, pack_infos, normalize_depth, early_stop_eps, alpha_thre)
+def composite(alpha, t, pack_infos, rgb=None, nablas=None, normalize_depth=True, early_stop_eps=1e-4, alpha_thre=0.0, ray_index=None,
+              n_rays=None):
+    """-> (vw [K], mask [P], depth [P], rgb [P,3] | None, normals [P,3] | None); differentiable wrt alpha, rgb, nablas.
+    With `ray_index` [P] and `n_rays`, the per-ray outputs are whole-image buffers [n_rays(,3)] written at ray_index (zeros elsewhere)."""
+    vw, mask, depth, rgb_o, nab_o = _Composite.apply(alpha, t, rgb, nablas, pack_infos, normalize_depth, early_stop_eps, alpha_thre,
+                                                     ray_index, n_rays)
     return vw, mask, depth, (rgb_o if rgb is not None else None), (nab_o if nablas is not None else None)

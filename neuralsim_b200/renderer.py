@@ -28,9 +28,9 @@ class SingleVolumeRenderer:
     def eval(self):
         return self.train(False)
 
-    def _volume_integration(self, volume_buffer, rendered):
+    def _volume_integration(self, volume_buffer, rendered, fresh=False):
         return volume_integration(volume_buffer, rendered, training=self.training,
-                                  depth_use_normalized_vw=self.config["depth_use_normalized_vw"], nablas_key="nablas_in_world")
+                                  depth_use_normalized_vw=self.config["depth_use_normalized_vw"], nablas_key="nablas_in_world", fresh=fresh)
 
     def ray_query(self, model: LoTDNeuSModel, rays_o, rays_d, rays_h_appear=None, near=None, far=None, return_buffer=True,
                   return_details=False) -> Dict:
@@ -55,7 +55,7 @@ class SingleVolumeRenderer:
             if "nablas" in vb:
                 # obj -> world rotation is the identity for a single static object (single_volume_renderer.py:262-276)
                 vb["nablas_in_world"] = vb["nablas"]
-            self._volume_integration(vb, rendered)
+            self._volume_integration(vb, rendered, fresh=True)
         if return_buffer:
             ret["volume_buffer"] = vb
         if return_details:
