@@ -175,6 +175,13 @@ int nsb_fused_sdf_rays(const nsb_lotd_meta *meta_host, const void *params_half, 
                        const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
                        int32_t max_level, float *sdf, void *stream);
 
+/* The same query for PACKED samples of coherent rays (an image): pack p = samples t[first_p .. first_p + n_p) of ray pack_ray[p]
+ * (NULL = p), pack_infos int64 [n_packs,2] = (first, n).  Traversal is ray-tiled (32 rays x 4 samples per tile) so that the lanes of
+ * a gather instruction sit in neighbouring cells; sdf is written to the packed slots -- results identical to nsb_fused_sdf_rays. */
+int nsb_fused_sdf_packs(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host, const float *rays_o,
+                        const float *rays_d, const int64_t *pack_infos, const int64_t *pack_ray, int64_t n_packs, const float *t,
+                        int32_t max_level, float *sdf, void *stream);
+
 /* Backward of nsb_fused_sdf / nsb_fused_sdf_rays wrt. the table and the decoder weights (nothing is saved by the
  * forward: features and pre-activations are recomputed).  Pass x != NULL, or x == NULL with (rays_o, rays_d, ridx, t).
  * All outputs are fp32 and ACCUMULATED into (caller zero-fills): d_grid[P], d_W1[W*F], d_b1[W], d_W2[W], d_b2[1].
@@ -241,10 +248,11 @@ int nsb_compact_samples(const uint8_t *selector, const int64_t *pack_infos, cons
 /* dst[idx[j]] = src[j] (unique idx; adjoint of the gather above). */
 int nsb_scatter_f32(const float *src, const int64_t *idx, int64_t n, float *dst, void *stream);
 /* AABBSpace.ray_test (nr3d_lib/models/spatial/aabb.py:71-99): normalised rays o_n, d_n [n,3], clamped slab interval near / far [n]
- * and flag[n] = the reference's validity mask.  center3 / radius3 are HOST pointers to 3 floats. */
+ * and flag[n] = the reference's validity mask.  center3 / radius3 are HOST pointers to 3 floats.  coherent_pairs (device, may be
+ * NULL) is incremented by the number of rays i whose origin and direction are within 1 % of ray i-1's (image-ordered rays). */
 int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64_t n, const float *center3, const float *radius3, int has_near,
                       float near_clip, int has_far, float far_clip, float *o_n, float *d_n, float *near, float *far, int32_t *flag,
-                      void *stream);
+                      int64_t *coherent_pairs, void *stream);
 /* rows idx[j] of (o_n, d_n, near, far) -> row j of the compacted outputs. */
 int nsb_gather_rays(const int64_t *idx, int64_t n, const float *o_n, const float *d_n, const float *near, const float *far, float *o_c,
                     float *d_c, float *near_c, float *far_c, void *stream);

@@ -15,11 +15,66 @@
 
 namespace nsb {
 
-template <bool FROM_RAYS, bool FAST_SP = true, bool FAST_CELLS = true>
+// MODE 0: points x[n,3];  MODE 1: x = o[ridx[i]] + d[ridx[i]] t[i] in the given (ray-major) order;
+// MODE 2: the same packed samples traversed RAY-TILED: a tile = 32 consecutive packs (rays) x 4 consecutive samples, lane = ray,
+//         warp = sample ordinal.  For coherent rays (an image) the 32 lanes of a gather instruction then sit in neighbouring
+//         cells -> few 128 B lines per request; the L1 tag stage (one line per ~2 cycles) is what bounds this kernel
+//         (profiles/r01d_ab.txt: 12.6 -> 7.4 ms on the boundary points of a frame).  sdf is written to the packed slot, so
+//         nothing downstream changes.  Incoherent rays (random training pixels) keep MODE 1: locality along the ray.
+struct SdfTile {
+    const PLMeta &m;
+    const __half *grid;
+    int max_level;
+    uint8_t *sA;
+    uint32_t a_addr, b_addr, idesc, tmem, lane_base;
+    uint64_t *mbar;
+    const float *sb1, *sW2;
+    float sb2;
+    SoftplusK spk;
+};
+
+// all 128 threads: my point's table coordinates -> my sdf (fp16-rounded, as fp32).  Ends with the CTA barrier that frees tile + TMEM.
+template <bool FAST_SP, bool FAST_CELLS>
+__device__ __forceinline__ float sdf_of_tile(const SdfTile &c, const float (&xs)[3], int tid, uint32_t &phase) {
+    gather_row_to_tile<kTile, FAST_CELLS>(c.m, c.grid, xs, c.max_level, c.sA, tid);
+    tc::fence_async_smem();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < NF / 16; ++ks)
+            tc::mma_f16_ss(c.tmem, tc::make_desc(c.a_addr + ks * 2 * (kTile * 16), kTile * 16, 128),
+                           tc::make_desc(c.b_addr + ks * 2 * (HW * 16), HW * 16, 128), c.idesc, ks > 0);
+        tc::commit(c.mbar);
+    }
+    tc::mbar_wait(c.mbar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+    float out = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < HW / 8; ++ch) {
+        float z[8];
+        tc::tmem_ld8(c.tmem + c.lane_base + ch * 8, z);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float zz = __half2float(__float2half_rn(z[j] + c.sb1[ch * 8 + j]));
+            float sp;
+            if (FAST_SP) sp = softplus_a(zz, c.spk);
+            else { const float zb = zz * c.spk.beta; sp = zb > 20.f ? zz : log1pf(expf(zb)) * (1.f / c.spk.beta); }
+            out = fmaf(__half2float(__float2half_rn(sp)), c.sW2[ch * 8 + j], out);
+        }
+    }
+    tc::fence_before_sync();               // TMEM reads done before the next tile's MMA overwrites Z
+    __syncthreads();
+    return __half2float(__float2half_rn(out + c.sb2));
+}
+
+template <int MODE, bool FAST_SP = false, bool FAST_CELLS = true>
 __global__ void __launch_bounds__(kTile)
 k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
                const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ridx,
-               const float *__restrict__ t, int64_t n, int max_level, float *__restrict__ sdf) {
+               const float *__restrict__ t, int64_t n, int max_level, float *__restrict__ sdf, const int64_t *__restrict__ pack_infos,
+               const int64_t *__restrict__ pack_ray, int64_t n_packs) {
     __shared__ __align__(1024) uint8_t sA[kTile * NF * 2];   // 8 KB : features, chunk-major core-matrix layout
     __shared__ __align__(1024) uint8_t sB[HW * NF * 2];      // 4 KB : W1 [64 x 32], same layout
     __shared__ float sb1[HW], sW2[HW];
@@ -27,7 +82,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_slot;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     stage_W1(dec, sB, tid);
     if (tid < HW) {
         sb1[tid] = tid < dec.width ? __half2float(dec.b1[tid]) : 0.f;
@@ -43,52 +98,51 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = tc::make_idesc(kTile, HW, 0, 0);
-    const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const SoftplusK spk(dec.beta);
+    const SdfTile ctx{m, grid, max_level, sA, tc::smem_u32(sA), tc::smem_u32(sB), tc::make_idesc(kTile, HW, 0, 0), tmem_slot,
+                      (uint32_t)(warp * 32) << 16, &mbar, sb1, sW2, sb2, SoftplusK(dec.beta)};
     uint32_t phase = 0;
 
-    const int64_t n_tiles = (n + kTile - 1) / kTile;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kTile + tid;
-        const bool valid = i < n;
-        float xs[3];
-        load_point(FROM_RAYS, x, rays_o, rays_d, ridx, t, i, valid, xs);
-        gather_row_to_tile<kTile, FAST_CELLS>(m, grid, xs, max_level, sA, tid);
-        tc::fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
+    if (MODE == 2) {
+        const int64_t n_groups = (n_packs + 31) / 32;
+        for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+            const int64_t p = g * 32 + lane;
+            int64_t first = 0, cnt = 0, ray = 0;
+            if (p < n_packs) { first = pack_infos[2 * p]; cnt = pack_infos[2 * p + 1]; ray = pack_ray ? pack_ray[p] : p; }
+            float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+            if (cnt > 0) {
 #pragma unroll
-            for (int ks = 0; ks < NF / 16; ++ks)
-                tc::mma_f16_ss(tmem, tc::make_desc(a_addr + ks * 2 * (kTile * 16), kTile * 16, 128),
-                               tc::make_desc(b_addr + ks * 2 * (HW * 16), HW * 16, 128), idesc, ks > 0);
-            tc::commit(&mbar);
-        }
-        tc::mbar_wait(&mbar, phase);
-        phase ^= 1;
-        tc::fence_after_sync();
-        float out = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < HW / 8; ++c) {
-            float z[8];
-            tc::tmem_ld8(tmem + lane_base + c * 8, z);
+                for (int q = 0; q < 3; ++q) { o[q] = rays_o[ray * 3 + q]; d[q] = rays_d[ray * 3 + q]; }
+            }
+            int max_n = (int)cnt;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float zz = __half2float(__float2half_rn(z[j] + sb1[c * 8 + j]));
-                float sp;
-                if (FAST_SP) sp = softplus_a(zz, spk);
-                else { const float zb = zz * spk.beta; sp = zb > 20.f ? zz : log1pf(expf(zb)) * (1.f / spk.beta); }
-                out = fmaf(__half2float(__float2half_rn(sp)), sW2[c * 8 + j], out);
+            for (int s = 16; s > 0; s >>= 1) max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, s));
+            for (int k0 = 0; k0 < max_n; k0 += kTile / 32) {
+                const int k = k0 + warp;
+                const bool valid = k < cnt;
+                float xs[3] = {0.f, 0.f, 0.f};
+                if (valid) {
+                    const float tt = t[first + k];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) xs[q] = __fmaf_rn(d[q], tt, o[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) xs[q] = fminf(fmaxf(__fmaf_rn(xs[q], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
+                const float v = sdf_of_tile<FAST_SP, FAST_CELLS>(ctx, xs, tid, phase);
+                if (valid) sdf[first + k] = v;
             }
         }
-        if (valid) sdf[i] = __half2float(__float2half_rn(out + sb2));
-        tc::fence_before_sync();           // TMEM reads done before the next tile's MMA overwrites Z
-        __syncthreads();
+    } else {
+        const int64_t n_tiles = (n + kTile - 1) / kTile;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t i = tile * kTile + tid;
+            const bool valid = i < n;
+            float xs[3];
+            load_point(MODE == 1, x, rays_o, rays_d, ridx, t, i, valid, xs);
+            const float v = sdf_of_tile<FAST_SP, FAST_CELLS>(ctx, xs, tid, phase);
+            if (valid) sdf[i] = v;
+        }
     }
-    if (warp == 0) tc::tmem_free<64>(tmem);
+    if (warp == 0) tc::tmem_free<64>(ctx.tmem);
 }
 
 // =====================================================================================================================
@@ -270,27 +324,37 @@ static inline unsigned persistent_grid(int64_t n, int ctas_per_sm) {
     return (unsigned)(n_tiles < wave ? n_tiles : wave);
 }
 
+template <int MODE>
+static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta &m, const __half *g, const DecoderDevTC &d, const float *x, const float *ro,
+                       const float *rd, const int64_t *ridx, const float *t, int64_t n, int ml, float *sdf, const int64_t *pi, const int64_t *pr, int64_t np) {
+    // default: libm softplus (its longer epilogue keeps fewer warps in the gather phase at once -> less L1 thrash; profiles/r01d_ab.txt)
+    if (variant == 1) k_fused_sdf_tc<MODE, true, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+    else if (variant == 2) k_fused_sdf_tc<MODE, false, false><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+    else k_fused_sdf_tc<MODE, false, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+}
+
+// mode 0: x[n,3];  1: (rays_o, rays_d, ridx, t)[n];  2: ray-tiled packs (pack_infos[n_packs,2], pack_ray[n_packs] or NULL, t, sdf packed)
 extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *params_half, const nsb_sdf_decoder *dec, const float *x,
                                        const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
-                                       int32_t max_level, float *sdf, void *stream, int from_rays) {
+                                       int32_t max_level, float *sdf, void *stream, int mode, const int64_t *pack_infos,
+                                       const int64_t *pack_ray, int64_t n_packs) {
     PLMeta m;
     if (make_plmeta(meta, &m)) return 2;
     NSB_REQUIRE(m.n_pseudo == 16 && m.F == 2 && m.D == 3 && plmeta_two_feature_cells(m), "nsb_fused_sdf (tensor-core): built for 16 x 2 LoTD features in 3-D");
     NSB_REQUIRE(dec->width >= 1 && dec->width <= 64, "nsb_fused_sdf (tensor-core): decoder width must be <= 64");
     DecoderDevTC d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2, dec->width,
                    dec->beta};
-    const unsigned grid = persistent_grid(n, 8);           // <= 8 resident CTAs/SM (TMEM: 8 x 64 columns)
+    // NSB_SDF_VARIANT / NSB_SDF_CTAS: profiling switches (profiles/ab_gather.py); 1 = SFU softplus, 2 = generic corner addressing
+    const int variant = getenv("NSB_SDF_VARIANT") ? atoi(getenv("NSB_SDF_VARIANT")) : 0;
+    const int ctas = getenv("NSB_SDF_CTAS") ? atoi(getenv("NSB_SDF_CTAS")) : 6;      // <= 8 (TMEM: 8 x 64 columns); 6 measured best
     cudaStream_t s = (cudaStream_t)stream;
     const int ml = max_level < 0 ? -1 : max_level;
-    // NSB_SDF_VARIANT (profiling only, profiles/ab_gather.py): bit 0 = libm softplus, bit 1 = generic corner addressing
-    const int variant = getenv("NSB_SDF_VARIANT") ? atoi(getenv("NSB_SDF_VARIANT")) : 0;
-    const int ctas = getenv("NSB_SDF_CTAS") ? atoi(getenv("NSB_SDF_CTAS")) : 8;
-    const unsigned g2 = persistent_grid(n, ctas);
-    if (from_rays && variant == 1) k_fused_sdf_tc<true, false, true><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
-    else if (from_rays && variant == 2) k_fused_sdf_tc<true, true, false><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
-    else if (from_rays && variant == 3) k_fused_sdf_tc<true, false, false><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
-    else if (from_rays) k_fused_sdf_tc<true><<<g2, kTile, 0, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf);
-    else k_fused_sdf_tc<false><<<grid, kTile, 0, s>>>(m, (const __half *)params_half, d, x, nullptr, nullptr, nullptr, nullptr, n, ml, sdf);
+    const __half *g = (const __half *)params_half;
+    if (mode == 2) {
+        const int64_t groups = (n_packs + 31) / 32, wave = (int64_t)sm_count() * ctas;
+        launch_sdf<2>(variant, (unsigned)(groups < wave ? groups : wave), s, m, g, d, nullptr, rays_o, rays_d, nullptr, t, n, ml, sdf, pack_infos, pack_ray, n_packs);
+    } else if (mode == 1) launch_sdf<1>(variant, persistent_grid(n, ctas), s, m, g, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf, nullptr, nullptr, 0);
+    else launch_sdf<0>(variant, persistent_grid(n, ctas), s, m, g, d, x, nullptr, nullptr, nullptr, nullptr, n, ml, sdf, nullptr, nullptr, 0);
     return check_launch("nsb_fused_sdf(tc)");
 }
 

@@ -23,30 +23,36 @@ __device__ __forceinline__ int64_t nwarps_() { return ((int64_t)gridDim.x * bloc
 // counts[N] (int32, >= 0)  ->  first[N] (exclusive prefix sum), and for the non-zero entries, in order:
 // nz_index[j] = i, nz_pack[j] = (first_i, counts_i) (int64), optionally gathered values nz_src[j] = src[i];
 // info2[N,2] = (first_i, counts_i) int32 (the reference's `packed_info`); totals = (sum, number of non-zeros).
-constexpr int kScanT = 1024;
+constexpr int kScanT = 1024, kScanI = 8;                  // one CTA, 8 consecutive items per thread and sweep
 __global__ void __launch_bounds__(kScanT)
 k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int32_t *__restrict__ first, int32_t *__restrict__ info2,
               int64_t *__restrict__ nz_index, int64_t *__restrict__ nz_pack, const int64_t *__restrict__ src, int64_t *__restrict__ nz_src,
               int64_t *__restrict__ totals) {
     __shared__ int64_t s_sum[32];
     __shared__ int32_t s_nz[32];
-    __shared__ int64_t carry_sum;
-    __shared__ int32_t carry_nz;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry_sum = 0; carry_nz = 0; }
-    __syncthreads();
-    for (int64_t base = 0; base < n; base += kScanT) {
-        const int64_t i = base + tid;
-        const int32_t c = i < n ? counts[i] : 0;
-        const int32_t z = c > 0 ? 1 : 0;
-        int64_t ps = c;
-        int32_t pz = z;
+    int64_t carry_sum = 0;                                // every thread keeps the running totals (uniform)
+    int32_t carry_nz = 0;
+    for (int64_t base = 0; base < n; base += (int64_t)kScanT * kScanI) {
+        const int64_t i0 = base + (int64_t)tid * kScanI;
+        int32_t c[kScanI];
+        int64_t ps = 0;
+        int32_t pz = 0;
+#pragma unroll
+        for (int k = 0; k < kScanI; ++k) {
+            c[k] = (i0 + k < n) ? counts[i0 + k] : 0;
+            ps += c[k];
+            pz += c[k] > 0 ? 1 : 0;
+        }
+        const int64_t tsum = ps;
+        const int32_t tnz = pz;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int64_t a = __shfl_up_sync(0xffffffffu, ps, o);
             const int32_t b = __shfl_up_sync(0xffffffffu, pz, o);
             if (lane >= o) { ps += a; pz += b; }
         }
+        __syncthreads();                                  // s_sum / s_nz of the previous sweep have been read
         if (lane == 31) { s_sum[warp] = ps; s_nz[warp] = pz; }
         __syncthreads();
         if (warp == 0) {
@@ -62,20 +68,25 @@ k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int32_t *__restrict
             s_nz[lane] = b;
         }
         __syncthreads();
-        const int64_t excl = carry_sum + (warp ? s_sum[warp - 1] : 0) + ps - c;
-        const int32_t rank = carry_nz + (warp ? s_nz[warp - 1] : 0) + pz - z;
-        if (i < n) {
-            if (first) first[i] = (int32_t)excl;
-            if (info2) { info2[2 * i] = (int32_t)excl; info2[2 * i + 1] = c; }
-            if (z) {
-                if (nz_index) nz_index[rank] = i;
-                if (nz_pack) { nz_pack[2 * rank] = excl; nz_pack[2 * rank + 1] = c; }
-                if (nz_src) nz_src[rank] = src[i];
+        int64_t excl = carry_sum + (warp ? s_sum[warp - 1] : 0) + ps - tsum;
+        int32_t rank = carry_nz + (warp ? s_nz[warp - 1] : 0) + pz - tnz;
+#pragma unroll
+        for (int k = 0; k < kScanI; ++k) {
+            const int64_t i = i0 + k;
+            if (i < n) {
+                if (first) first[i] = (int32_t)excl;
+                if (info2) { info2[2 * i] = (int32_t)excl; info2[2 * i + 1] = c[k]; }
+                if (c[k] > 0) {
+                    if (nz_index) nz_index[rank] = i;
+                    if (nz_pack) { nz_pack[2 * rank] = excl; nz_pack[2 * rank + 1] = c[k]; }
+                    if (nz_src) nz_src[rank] = src[i];
+                    ++rank;
+                }
             }
+            excl += c[k];
         }
-        __syncthreads();
-        if (tid == 0) { carry_sum += s_sum[31]; carry_nz += s_nz[31]; }
-        __syncthreads();
+        carry_sum += s_sum[31];
+        carry_nz += s_nz[31];
     }
     if (tid == 0) { totals[0] = carry_sum; totals[1] = carry_nz; }
 }
@@ -228,9 +239,21 @@ struct RayTestArgs {
 
 __global__ void __launch_bounds__(256)
 k_ray_test_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n, const RayTestArgs a, float *__restrict__ o_n,
-                float *__restrict__ d_n, float *__restrict__ near, float *__restrict__ far, int32_t *__restrict__ flag) {
+                float *__restrict__ d_n, float *__restrict__ near, float *__restrict__ far, int32_t *__restrict__ flag,
+                unsigned long long *__restrict__ coherent_pairs) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int close = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (coherent_pairs && i > 0) {                   // is ray i a neighbour of ray i-1 (image order)?  -> traversal order of the queries
+            float dd = 0.f, od = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                dd = fmaxf(dd, fabsf(rays_d[i * 3 + d] - rays_d[(i - 1) * 3 + d]));
+                od = fmaxf(od, fabsf(rays_o[i * 3 + d] - rays_o[(i - 1) * 3 + d]) / a.r[d]);
+            }
+            const float len = fmaxf(fmaxf(fabsf(rays_d[i * 3]), fabsf(rays_d[i * 3 + 1])), fabsf(rays_d[i * 3 + 2]));
+            close += (dd <= 0.01f * len && od <= 0.01f) ? 1u : 0u;
+        }
         float tn = 0.f, tf = 0.f;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -250,6 +273,10 @@ k_ray_test_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays
         near[i] = tn;
         far[i] = tf;
         flag[i] = m ? 1 : 0;
+    }
+    if (coherent_pairs) {
+        close = __reduce_add_sync(0xffffffffu, close);
+        if ((threadIdx.x & 31) == 0 && close) atomicAdd(coherent_pairs, (unsigned long long)close);
     }
 }
 
@@ -328,11 +355,11 @@ extern "C" int nsb_scatter_f32(const float *src, const int64_t *idx, int64_t n, 
 
 extern "C" int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64_t n, const float *center3, const float *radius3, int has_near,
                                  float near_clip, int has_far, float far_clip, float *o_n, float *d_n, float *near, float *far, int32_t *flag,
-                                 void *stream) {
+                                 int64_t *coherent_pairs, void *stream) {
     if (n == 0) return 0;
     NSB_REQUIRE(rays_o && rays_d && center3 && radius3 && o_n && d_n && near && far && flag, "nsb_ray_test_aabb: NULL argument");
     RayTestArgs a{{center3[0], center3[1], center3[2]}, {radius3[0], radius3[1], radius3[2]}, near_clip, far_clip, has_near, has_far};
-    k_ray_test_aabb<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(rays_o, rays_d, n, a, o_n, d_n, near, far, flag);
+    k_ray_test_aabb<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(rays_o, rays_d, n, a, o_n, d_n, near, far, flag, (unsigned long long *)coherent_pairs);
     return check_launch("nsb_ray_test_aabb");
 }
 

@@ -144,12 +144,17 @@ class _FusedSDF(autograd.Function):
         grid16, dec = owner._fused_state()
         meta = owner.encoding.meta
         if isinstance(pts, tuple):
-            ridx, t, rays_o, rays_d = pts
+            ridx, t, rays_o, rays_d, packs = pts
             n = t.numel()
             sdf = torch.empty(n, dtype=torch.float32, device=t.device)
             with L.KERNEL_TIMER.time("fused_sdf_fwd", n):
-                L.check(L.lib().nsb_fused_sdf_rays(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
-                                                   L.ptr(ridx, "i64"), L.ptr(t, "f32"), L.c_i64(n), L.c_i32(max_level), L.ptr(sdf), L.stream_ptr()), "fused_sdf")
+                if packs is not None:          # coherent rays: ray-tiled traversal of the same packed samples
+                    L.check(L.lib().nsb_fused_sdf_packs(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
+                                                        L.ptr(packs[0], "i64"), L.ptr(packs[1], "i64", allow_none=True), L.c_i64(packs[0].shape[0]),
+                                                        L.ptr(t, "f32"), L.c_i32(max_level), L.ptr(sdf), L.stream_ptr()), "fused_sdf_packs")
+                else:
+                    L.check(L.lib().nsb_fused_sdf_rays(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
+                                                       L.ptr(ridx, "i64"), L.ptr(t, "f32"), L.c_i64(n), L.c_i32(max_level), L.ptr(sdf), L.stream_ptr()), "fused_sdf")
         else:
             n = pts.shape[0]
             sdf = torch.empty(n, dtype=torch.float32, device=pts.device)
@@ -181,7 +186,7 @@ class _FusedSDF(autograd.Function):
         if sparse:
             d_sdf = d_sdf[keep]
         if isinstance(ctx.pts, tuple):
-            ridx, t, rays_o, rays_d = ctx.pts
+            ridx, t, rays_o, rays_d, _packs = ctx.pts
             if sparse:
                 ridx, t = ridx[keep], t[keep]
             args = (None, L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"), L.ptr(ridx, "i64"), L.ptr(t, "f32"))
@@ -239,13 +244,13 @@ class LoTDSDF(nn.Module):
                               d[0].weight, d[0].bias, d[1].weight, d[1].bias)
         return sdf.view(prefix)
 
-    def fused_sdf_rays_autograd(self, ridx, t, rays_o, rays_d, max_level: int = None):
+    def fused_sdf_rays_autograd(self, ridx, t, rays_o, rays_d, max_level: int = None, packs=None):
         d = self.decoder.layers
         shape = t.shape
         if t.dim() == 2:
             ridx = ridx.unsqueeze(-1).expand(shape)
         pts = (ridx.reshape(-1).contiguous().long(), t.detach().reshape(-1).contiguous().float(), rays_o.detach().contiguous(),
-               rays_d.detach().contiguous())
+               rays_d.detach().contiguous(), packs)
         sdf = _FusedSDF.apply(self, pts, self._ml(max_level), self.encoding.flattened_params, d[0].weight, d[0].bias, d[1].weight, d[1].bias)
         return sdf.view(shape)
 
@@ -297,9 +302,18 @@ class LoTDSDF(nn.Module):
         return sdf.view(prefix)
 
     @torch.no_grad()
-    def fused_sdf_rays(self, ridx, t, rays_o, rays_d, max_level: int = None):
+    def fused_sdf_rays(self, ridx, t, rays_o, rays_d, max_level: int = None, packs=None):
         grid16, dec = self._fused_state()
         shape = t.shape
+        if packs is not None:
+            tf = t.reshape(-1).contiguous().float()
+            sdf = torch.empty(tf.shape[0], dtype=torch.float32, device=tf.device)
+            ml = self.encoding.meta.n_levels if (max_level or self.encoding.max_level) is None else int(max_level or self.encoding.max_level)
+            with L.KERNEL_TIMER.time("lotd_gather", tf.shape[0]):
+                L.check(L.lib().nsb_fused_sdf_packs(self.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o.contiguous(), "f32"),
+                                                    L.ptr(rays_d.contiguous(), "f32"), L.ptr(packs[0], "i64"), L.ptr(packs[1], "i64", allow_none=True),
+                                                    L.c_i64(packs[0].shape[0]), L.ptr(tf, "f32"), L.c_i32(ml), L.ptr(sdf), L.stream_ptr()), "fused_sdf_packs")
+            return sdf.view(shape)
         if t.dim() == 2:
             ridx = ridx.unsqueeze(-1).expand(shape)
         ridx, tf = ridx.reshape(-1).contiguous().long(), t.reshape(-1).contiguous().float()

@@ -65,13 +65,15 @@ class LoTDNeuS(nn.Module):
             return self.implicit_surface(x, return_h=True, max_level=self.max_level)
         return self.implicit_surface.forward_sdf(x, max_level=self.max_level)
 
-    def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d):
-        """sdf at o[ridx] + d[ridx]*t.  No-grad calls never materialise the points (fused kernel)."""
+    def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d, packs=None):
+        """sdf at o[ridx] + d[ridx]*t.  No-grad calls never materialise the points (fused kernel).
+        packs = (pack_infos [P,2], ray of every pack [P] | None): the samples are the packs of coherent (image-ordered) rays -> the
+        fused kernel walks them ray-tiled; same values."""
         if self.implicit_surface._fusable():
             if not torch.is_grad_enabled():
-                return dict(sdf=self.implicit_surface.fused_sdf_rays(ridx, t, rays_o, rays_d, max_level=self.max_level))
+                return dict(sdf=self.implicit_surface.fused_sdf_rays(ridx, t, rays_o, rays_d, max_level=self.max_level, packs=packs))
             if not (t.requires_grad or rays_o.requires_grad or rays_d.requires_grad):
-                return dict(sdf=self.implicit_surface.fused_sdf_rays_autograd(ridx, t, rays_o, rays_d, max_level=self.max_level))
+                return dict(sdf=self.implicit_surface.fused_sdf_rays_autograd(ridx, t, rays_o, rays_d, max_level=self.max_level, packs=packs))
         if t.dim() == 2:
             x = torch.addcmul(rays_o[ridx].unsqueeze(-2), rays_d[ridx].unsqueeze(-2), t.unsqueeze(-1)).flatten(0, -2)
             return dict(sdf=self.forward_sdf(x)["sdf"].view(t.shape))
@@ -161,8 +163,8 @@ class LoTDNeuSModel(LoTDNeuS):
             self.accel.collect_samples(x, val=ret["sdf"].detach())
         return ret
 
-    def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d):
-        ret = super().forward_sdf_on_rays(ridx, t, rays_o, rays_d)
+    def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d, packs=None):
+        ret = super().forward_sdf_on_rays(ridx, t, rays_o, rays_d, packs=packs)
         if self.training and self.accel is not None and self.accel.occ.should_collect_samples:
             # the fused query never materialised the points; rebuild them only to feed the accel's statistics
             r = ridx.unsqueeze(-1).expand(t.shape) if t.dim() == 2 else ridx

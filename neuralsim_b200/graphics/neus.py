@@ -111,19 +111,21 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, with_rgb, with_
         return None
     ridx_hit, pinfo_march, depth_samples, ridx = marched
     pack_infos = pinfo_march
+    coherent = bool(ray_tested.get("rays_coherent", False))      # image-ordered rays: ray-tiled traversal inside the SDF kernel
     with torch.no_grad():
-        sdf = model.forward_sdf_on_rays(ridx, depth_samples, rays_o, rays_d)["sdf"].to(dtype)
+        sdf = model.forward_sdf_on_rays(ridx, depth_samples, rays_o, rays_d, packs=(pack_infos, ridx_hit) if coherent else None)["sdf"].to(dtype)
         fine_stages = []
         for i, factor in enumerate(factors):
             cdf = neus_fused.upsample_cdf(sdf, depth_samples, pack_infos, upsample_inv_s * factor, use_estimate_alpha)
             fine = neus_fused.sample_cdf_uniform(depth_samples, cdf, pack_infos, num_fine[i])
             fine_stages.append(fine)
             if i < n_stage - 1:         # (the reference also merges after the last stage; nothing reads that result)
-                sdf_fine = model.forward_sdf_on_rays(ridx_hit, fine, rays_o, rays_d)["sdf"].to(dtype).contiguous()
+                packs = (get_pack_infos_from_batch(ridx_hit.shape[0], fine.shape[1], device=fine.device), ridx_hit) if coherent else None
+                sdf_fine = model.forward_sdf_on_rays(ridx_hit, fine, rays_o, rays_d, packs=packs)["sdf"].to(dtype).contiguous()
                 depth_samples, sdf, pack_infos = neus_fused.merge_sorted_vals(depth_samples, sdf, pack_infos, fine, sdf_fine)
         fine_all = torch.cat(fine_stages, dim=-1) if n_stage > 1 else fine_stages[0]
         d1, mid, ridx_all, pinfo = neus_fused.assemble_boundary(depths_coarse_1.contiguous(), ridx_hit, fine_all.contiguous())
-    sdf_b = model.forward_sdf_on_rays(ridx_all, d1, rays_o, rays_d)["sdf"].to(dtype)
+    sdf_b = model.forward_sdf_on_rays(ridx_all, d1, rays_o, rays_d, packs=(pinfo, None) if coherent else None)["sdf"].to(dtype)
     comp = neus_fused.neus_alpha_compact(sdf_b, forward_inv_s, pinfo, ridx_all, mid, rays_inds)
     if comp is None:
         return dict(type="empty", rays_inds_hit=[]), {}

@@ -110,7 +110,7 @@ class _GatherUnique(torch.autograd.Function):
 
 
 @torch.no_grad()
-def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False, want_pack=False, src=None):
+def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False, want_pack=False, src=None, totals=None):
     """One launch + ONE host read: exclusive scan of int32 counts and compaction of the non-zero entries.
     -> dict(total, n_nonzero, first?, info2?, index?, pack?, src?) with the compacted outputs already sliced."""
     n, dev = counts.shape[0], counts.device
@@ -119,12 +119,14 @@ def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False,
     index = torch.empty(n, dtype=torch.int64, device=dev) if want_index else None
     pack = torch.empty(n, 2, dtype=torch.int64, device=dev) if want_pack else None
     nz_src = torch.empty(n, dtype=torch.int64, device=dev) if src is not None else None
-    totals = torch.empty(2, dtype=torch.int64, device=dev)
+    if totals is None:               # else: a caller-owned int64[>=2] whose further slots another kernel filled; read in the same sync
+        totals = torch.empty(2, dtype=torch.int64, device=dev)
     L.check(L.lib().nsb_scan_counts(L.ptr(counts, "i32"), L.c_i64(n), L.ptr(first, allow_none=True), L.ptr(info2, allow_none=True),
                                     L.ptr(index, allow_none=True), L.ptr(pack, allow_none=True), L.ptr(src, "i64", allow_none=True),
                                     L.ptr(nz_src, allow_none=True), L.ptr(totals), L.stream_ptr()), "scan_counts")
-    total, nnz = totals.tolist()                      # the one host sync: output sizes are data dependent
-    out = dict(total=int(total), n_nonzero=int(nnz), first=first, info2=info2)
+    host = totals.tolist()                            # the one host sync: output sizes are data dependent
+    total, nnz = host[0], host[1]
+    out = dict(total=int(total), n_nonzero=int(nnz), first=first, info2=info2, extra=host[2:])
     out["index"] = index[:nnz] if index is not None else None
     out["pack"] = pack[:nnz] if pack is not None else None
     out["src"] = nz_src[:nnz] if nz_src is not None else None

@@ -31,7 +31,7 @@ def run(tag, reps=4):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         with torch.no_grad():
-            s = surf.fused_sdf_rays(ridx, t, ro, rd)
+            s = surf.fused_sdf_rays(ridx, t, ro, rd, packs=PACKS)
         b.record()
         torch.cuda.synchronize()
         if i:
@@ -41,19 +41,32 @@ def run(tag, reps=4):
     return s
 
 
+pinfo = torch.stack([torch.arange(R, device=dev) * 65, torch.full((R,), 65, device=dev)], 1).contiguous()
+PACKS = None
+
+
+def run_packs(tag):
+    global PACKS
+    PACKS = (pinfo, None)
+    s = run(tag)
+    PACKS = None
+    return s
+
+
 ref = None
-for variant, name in ((0, "sfu softplus + cell addressing"), (1, "libm softplus + cell addressing"), (2, "sfu softplus + generic addressing"),
-                      (3, "libm softplus + generic addressing (r01b)")):
-    for ctas in (8, 6, 4):
+for variant, name in ((0, "libm softplus + cell addressing"), (1, "sfu softplus + cell addressing")):
+    for ctas in (8, 6, 4, 3):
         os.environ["NSB_SDF_VARIANT"], os.environ["NSB_SDF_CTAS"] = str(variant), str(ctas)
         s = run(f"{name}, {ctas} CTA/SM")
+        s2 = run_packs(f"{name}, {ctas} CTA/SM, RAY-TILED")
+        print("    tiled == ray-major:", bool(torch.equal(s, s2)), flush=True)
         if ref is None:
             ref = s
         else:
             dd = (s - ref).abs()
             print(f"    vs variant 0: max |d| {float(dd.max()):.3e}, differing {float((dd > 0).float().mean()) * 100:.3f} %", flush=True)
 # point order: the same points, pixel-patch-major (8x4 pixel tiles x 65 depths) instead of ray-major
-os.environ["NSB_SDF_VARIANT"], os.environ["NSB_SDF_CTAS"] = "0", "8"
+os.environ["NSB_SDF_VARIANT"], os.environ["NSB_SDF_CTAS"] = "0", "6"
 perm = torch.randperm(t.numel(), device=dev)
 ridx_r, t_r = ridx[perm].contiguous(), t[perm].contiguous()
 ridx, t = ridx_r, t_r
