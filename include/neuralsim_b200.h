@@ -229,9 +229,12 @@ int nsb_composite_backward(const float *alpha, const float *t, const float *rgb,
  * nsb_scan_counts: one launch for cumsum + nonzero + stack of the reference's wrappers (occgrid_raymarch.py:60-75,
  *   pack_ops.py:286-291): first[n] = exclusive prefix sum of counts; info2[n,2] = (first, count) int32 (`packed_info`);
  *   for the non-zero entries in order: nz_index[j] = i, nz_pack[j] = (first_i, count_i), nz_src[j] = src[i];
- *   totals[2] = (sum of counts, number of non-zero entries), on the device.  Outputs other than totals may be NULL. */
+ *   totals[2] = (sum of counts, number of non-zero entries), on the device.  Outputs other than totals may be NULL.
+ *   workspace_zeroed: nsb_scan_workspace_bytes() of device memory, zero-filled before every call. */
 int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first, int32_t *info2, int64_t *nz_index, int64_t *nz_pack,
-                    const int64_t *src, int64_t *nz_src, int64_t *totals, void *stream);
+                    const int64_t *src, int64_t *nz_src, int64_t *totals, void *workspace_zeroed, void *stream);
+/* bytes of the zero-filled device workspace nsb_scan_counts needs (inter-block totals + ready flags of its one-launch scan) */
+int64_t nsb_scan_workspace_bytes(void);
 /* merge_two_packs_sorted_aligned (pack_ops.py:529-560) fused with the scatter of the payloads: packs of (dep_a, sdf_a) and rows
  * of (dep_b, sdf_b)[n_packs, n_b], both sorted by depth -> merged (dep_m, sdf_m) and pack_infos_m.  sdf_* may be NULL. */
 int nsb_merge_sorted_vals(const float *dep_a, const float *sdf_a, const int64_t *pack_infos_a, const float *dep_b, const float *sdf_b,
@@ -249,7 +252,7 @@ int nsb_compact_samples(const uint8_t *selector, const int64_t *pack_infos, cons
 int nsb_scatter_f32(const float *src, const int64_t *idx, int64_t n, float *dst, void *stream);
 /* AABBSpace.ray_test (nr3d_lib/models/spatial/aabb.py:71-99): normalised rays o_n, d_n [n,3], clamped slab interval near / far [n]
  * and flag[n] = the reference's validity mask.  center3 / radius3 are HOST pointers to 3 floats.  coherent_pairs (device, may be
- * NULL) is incremented by the number of rays i whose origin and direction are within 1 % of ray i-1's (image-ordered rays). */
+ * NULL) is incremented by the number of rays i whose origin and direction are within 3 % of ray i-1's (image-ordered rays). */
 int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64_t n, const float *center3, const float *radius3, int has_near,
                       float near_clip, int has_far, float far_clip, float *o_n, float *d_n, float *near, float *far, int32_t *flag,
                       int64_t *coherent_pairs, void *stream);

@@ -636,8 +636,8 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
             *reinterpret_cast<uint4 *>(sT + kTileBytes + c * kChunk + tid * 16) = tc::pack8_f16(uu);
         }
         // dg = J gin (fp16), level by level, into my row of Ge
-#pragma unroll 1
-        for (uint32_t p = 0; p < 16; ++p) {
+#pragma unroll 2
+        for (uint32_t p = 0; p < 16; ++p) {               // two levels per trip: 16 independent corner loads in flight
             uint32_t packed = 0;
             if ((int)m.level[p] <= max_level) {
                 float J0[3], J1[3];

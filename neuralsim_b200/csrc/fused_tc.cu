@@ -34,9 +34,9 @@ struct SdfTile {
 };
 
 // all 128 threads: my point's table coordinates -> my sdf (fp16-rounded, as fp32).  Ends with the CTA barrier that frees tile + TMEM.
-template <bool FAST_SP, bool FAST_CELLS>
+template <bool FAST_SP, int UNROLL>
 __device__ __forceinline__ float sdf_of_tile(const SdfTile &c, const float (&xs)[3], int tid, uint32_t &phase) {
-    gather_row_to_tile<kTile, FAST_CELLS>(c.m, c.grid, xs, c.max_level, c.sA, tid);
+    gather_row_to_tile<kTile, UNROLL>(c.m, c.grid, xs, c.max_level, c.sA, tid);
     tc::fence_async_smem();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ float sdf_of_tile(const SdfTile &c, const float (&xs)
     return __half2float(__float2half_rn(out + c.sb2));
 }
 
-template <int MODE, bool FAST_SP = false, bool FAST_CELLS = true>
+template <int MODE, bool FAST_SP = false, int UNROLL = 2>
 __global__ void __launch_bounds__(kTile)
 k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
                const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ridx,
@@ -127,7 +127,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
                 }
 #pragma unroll
                 for (int q = 0; q < 3; ++q) xs[q] = fminf(fmaxf(__fmaf_rn(xs[q], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
-                const float v = sdf_of_tile<FAST_SP, FAST_CELLS>(ctx, xs, tid, phase);
+                const float v = sdf_of_tile<FAST_SP, UNROLL>(ctx, xs, tid, phase);
                 if (valid) sdf[first + k] = v;
             }
         }
@@ -138,7 +138,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
             const bool valid = i < n;
             float xs[3];
             load_point(MODE == 1, x, rays_o, rays_d, ridx, t, i, valid, xs);
-            const float v = sdf_of_tile<FAST_SP, FAST_CELLS>(ctx, xs, tid, phase);
+            const float v = sdf_of_tile<FAST_SP, UNROLL>(ctx, xs, tid, phase);
             if (valid) sdf[i] = v;
         }
     }
@@ -327,10 +327,14 @@ static inline unsigned persistent_grid(int64_t n, int ctas_per_sm) {
 template <int MODE>
 static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta &m, const __half *g, const DecoderDevTC &d, const float *x, const float *ro,
                        const float *rd, const int64_t *ridx, const float *t, int64_t n, int ml, float *sdf, const int64_t *pi, const int64_t *pr, int64_t np) {
-    // default: libm softplus (its longer epilogue keeps fewer warps in the gather phase at once -> less L1 thrash; profiles/r01d_ab.txt)
-    if (variant == 1) k_fused_sdf_tc<MODE, true, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
-    else if (variant == 2) k_fused_sdf_tc<MODE, false, false><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
-    else k_fused_sdf_tc<MODE, false, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+    // ray-major order: libm softplus (its longer epilogue keeps fewer warps in the gather phase at once -> less L1 thrash);
+    // ray-tiled order: SFU softplus (gathers coalesce, the kernel is issue-bound again).  profiles/r01e_ab.txt
+    // variants: 0 libm / 2 levels per trip, 1 SFU / 2, 2 libm / 1, 3 SFU / 1
+    if (variant < 0) variant = (MODE == 2) ? 1 : 2;
+    if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+    else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+    else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+    else k_fused_sdf_tc<MODE, false, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
 }
 
 // mode 0: x[n,3];  1: (rays_o, rays_d, ridx, t)[n];  2: ray-tiled packs (pack_infos[n_packs,2], pack_ray[n_packs] or NULL, t, sdf packed)
@@ -344,8 +348,8 @@ extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *pa
     NSB_REQUIRE(dec->width >= 1 && dec->width <= 64, "nsb_fused_sdf (tensor-core): decoder width must be <= 64");
     DecoderDevTC d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2, dec->width,
                    dec->beta};
-    // NSB_SDF_VARIANT / NSB_SDF_CTAS: profiling switches (profiles/ab_gather.py); 1 = SFU softplus, 2 = generic corner addressing
-    const int variant = getenv("NSB_SDF_VARIANT") ? atoi(getenv("NSB_SDF_VARIANT")) : 0;
+    // NSB_SDF_VARIANT / NSB_SDF_CTAS: profiling switches (profiles/ab_gather.py); see launch_sdf
+    const int variant = getenv("NSB_SDF_VARIANT") ? atoi(getenv("NSB_SDF_VARIANT")) : -1;
     const int ctas = getenv("NSB_SDF_CTAS") ? atoi(getenv("NSB_SDF_CTAS")) : 6;      // <= 8 (TMEM: 8 x 64 columns); 6 measured best
     cudaStream_t s = (cudaStream_t)stream;
     const int ml = max_level < 0 ? -1 : max_level;

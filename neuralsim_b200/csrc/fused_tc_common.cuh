@@ -16,25 +16,25 @@ constexpr int kTile = 128;
 constexpr int NF = 32, HW = 64;           // features, hidden width (zero padded to 64)
 
 // the 16 levels of one point -> row `r` of a chunk-major [R x >=32] fp16 tile (4 bytes per level)
-template <int R, bool FAST_CELLS = true>
+// U levels per loop trip: the 8 U corner loads of a trip are independent, so U = 2 doubles the loads in flight per thread (the
+// latency-bound backward kernels run at 8-16 warps / SM); full unrolling is avoided on purpose (instruction cache, see fused_tc.cu).
+template <int R, int U = 2>
 __device__ __forceinline__ void gather_row_to_tile(const PLMeta &m, const __half *__restrict__ grid, const float (&xs)[3],
                                                    int max_level, uint8_t *tile, int r) {
 #pragma unroll 1
-    for (uint32_t p = 0; p < 16; ++p) {
-        uint32_t packed = 0;
-        if ((int)m.level[p] <= max_level) {
-            float w[8];
-            if (FAST_CELLS) {
-                uint32_t cell[8];
-                level_cells3(m, p, xs, cell, w);
-                packed = level_feat2_cells(level_cells_ptr(m, p, grid), cell, w);
-            } else {
-                uint32_t idx[8];
-                level_corners3(m, p, xs, idx, w);
-                packed = level_feat2(grid, idx, w);
-            }
+    for (uint32_t p0 = 0; p0 < 16; p0 += U) {
+        uint32_t cell[U][8];
+        float w[U][8];
+        uint32_t packed[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) level_cells3(m, p0 + u, xs, cell[u], w[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) packed[u] = level_feat2_cells(level_cells_ptr(m, p0 + u, grid), cell[u], w[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t p = p0 + u;
+            *reinterpret_cast<uint32_t *>(tile + (p >> 2) * (R * 16) + r * 16 + (p & 3) * 4) = ((int)m.level[p] <= max_level) ? packed[u] : 0u;
         }
-        *reinterpret_cast<uint32_t *>(tile + (p >> 2) * (R * 16) + r * 16 + (p & 3) * 4) = packed;
     }
 }
 

@@ -26,13 +26,19 @@ __device__ __forceinline__ void replay_chunk(float a, int lim, int lane, float e
     my_w = 0.f;
     my_sel = false;
     if (stopped) return;
-    for (int q = 0; q < lim; ++q) {
+    // only the samples with alpha > thre change T; walk those (most chunks of most rays have none: empty space).  The early-stop
+    // test `T < eps` of the reference runs before every sample; T only changes at the visited ones, so testing there (and once at
+    // the chunk's start) stops at exactly the same sample.
+    unsigned live = __ballot_sync(0xffffffffu, lane < lim && a > thre);
+    if (T < eps) { stopped = true; return; }
+    while (live) {
+        const int q = __ffs(live) - 1;
+        live &= live - 1;
         const float aq = __shfl_sync(0xffffffffu, a, q);
-        if (T < eps) { stopped = true; break; }
-        if (aq <= thre) continue;
         if (q == lane) { my_w = __fmul_rn(aq, T); my_sel = true; }
         T = __fmul_rn(T, __fsub_rn(1.f, aq));
         ++cnt;
+        if (T < eps) { stopped = (live != 0) || (q + 1 < lim); break; }
     }
 }
 

@@ -23,57 +23,99 @@ __device__ __forceinline__ int64_t nwarps_() { return ((int64_t)gridDim.x * bloc
 // counts[N] (int32, >= 0)  ->  first[N] (exclusive prefix sum), and for the non-zero entries, in order:
 // nz_index[j] = i, nz_pack[j] = (first_i, counts_i) (int64), optionally gathered values nz_src[j] = src[i];
 // info2[N,2] = (first_i, counts_i) int32 (the reference's `packed_info`); totals = (sum, number of non-zeros).
-constexpr int kScanT = 1024, kScanI = 8;                  // one CTA, 8 consecutive items per thread and sweep
+constexpr int kScanT = 1024, kScanI = 8, kScanMaxBlocks = 128;     // every block is resident (128 <= #SMs): spinning on predecessors is safe
+struct ScanWs {                                                      // zero-filled by the caller before every launch
+    long long sum[kScanMaxBlocks];
+    int nz[kScanMaxBlocks];
+    int flag[kScanMaxBlocks];
+};
+
+__device__ __forceinline__ void block_scan_pair(int64_t &ps, int32_t &pz, int lane, int warp, int64_t *s_sum, int32_t *s_nz) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t a = __shfl_up_sync(0xffffffffu, ps, o);
+        const int32_t b = __shfl_up_sync(0xffffffffu, pz, o);
+        if (lane >= o) { ps += a; pz += b; }
+    }
+    __syncthreads();                                      // s_sum / s_nz of the previous sweep have been read
+    if (lane == 31) { s_sum[warp] = ps; s_nz[warp] = pz; }
+    __syncthreads();
+    if (warp == 0) {
+        int64_t a = s_sum[lane];
+        int32_t b = s_nz[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t a2 = __shfl_up_sync(0xffffffffu, a, o);
+            const int32_t b2 = __shfl_up_sync(0xffffffffu, b, o);
+            if (lane >= o) { a += a2; b += b2; }
+        }
+        s_sum[lane] = a;
+        s_nz[lane] = b;
+    }
+    __syncthreads();
+}
+
+// Block b owns the contiguous segment [b seg, (b+1) seg): (1) segment totals -> published, (2) wait for the predecessors' totals,
+// (3) scan the segment with that carry.  One launch, a few microseconds for 10^5..10^6 counts.
 __global__ void __launch_bounds__(kScanT)
-k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int32_t *__restrict__ first, int32_t *__restrict__ info2,
-              int64_t *__restrict__ nz_index, int64_t *__restrict__ nz_pack, const int64_t *__restrict__ src, int64_t *__restrict__ nz_src,
-              int64_t *__restrict__ totals) {
+k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int64_t seg, ScanWs *__restrict__ ws, int32_t *__restrict__ first,
+              int32_t *__restrict__ info2, int64_t *__restrict__ nz_index, int64_t *__restrict__ nz_pack, const int64_t *__restrict__ src,
+              int64_t *__restrict__ nz_src, int64_t *__restrict__ totals) {
     __shared__ int64_t s_sum[32];
     __shared__ int32_t s_nz[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int64_t carry_sum = 0;                                // every thread keeps the running totals (uniform)
-    int32_t carry_nz = 0;
-    for (int64_t base = 0; base < n; base += (int64_t)kScanT * kScanI) {
+    __shared__ int64_t s_carry_sum;
+    __shared__ int32_t s_carry_nz;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    const int64_t lo = (int64_t)b * seg, hi = min(n, lo + seg);
+    // ---- (1) totals of my segment
+    int64_t ps = 0;
+    int32_t pz = 0;
+    for (int64_t i = lo + tid; i < hi; i += kScanT) { const int32_t c = counts[i]; ps += c; pz += c > 0 ? 1 : 0; }
+    block_scan_pair(ps, pz, lane, warp, s_sum, s_nz);
+    const int64_t my_sum = s_sum[31];
+    const int32_t my_nz = s_nz[31];
+    if (tid == 0) {
+        ws->sum[b] = my_sum;
+        ws->nz[b] = my_nz;
+        __threadfence();
+        atomicExch(&ws->flag[b], 1);
+    }
+    // ---- (2) carry = totals of the blocks before me
+    ps = 0;
+    pz = 0;
+    if (tid < b) {
+        while (atomicAdd(&ws->flag[tid], 0) == 0) {}
+        __threadfence();
+        ps = *((volatile long long *)&ws->sum[tid]);
+        pz = *((volatile int *)&ws->nz[tid]);
+    }
+    block_scan_pair(ps, pz, lane, warp, s_sum, s_nz);
+    if (tid == 0) { s_carry_sum = s_sum[31]; s_carry_nz = s_nz[31]; }
+    __syncthreads();
+    int64_t carry_sum = s_carry_sum;
+    int32_t carry_nz = s_carry_nz;
+    if (b == gridDim.x - 1 && tid == 0) { totals[0] = carry_sum + my_sum; totals[1] = carry_nz + my_nz; }
+    // ---- (3) scan my segment, kScanI consecutive items per thread and sweep
+    for (int64_t base = lo; base < hi; base += (int64_t)kScanT * kScanI) {
         const int64_t i0 = base + (int64_t)tid * kScanI;
         int32_t c[kScanI];
-        int64_t ps = 0;
-        int32_t pz = 0;
+        ps = 0;
+        pz = 0;
 #pragma unroll
         for (int k = 0; k < kScanI; ++k) {
-            c[k] = (i0 + k < n) ? counts[i0 + k] : 0;
+            c[k] = (i0 + k < hi) ? counts[i0 + k] : 0;
             ps += c[k];
             pz += c[k] > 0 ? 1 : 0;
         }
         const int64_t tsum = ps;
         const int32_t tnz = pz;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int64_t a = __shfl_up_sync(0xffffffffu, ps, o);
-            const int32_t b = __shfl_up_sync(0xffffffffu, pz, o);
-            if (lane >= o) { ps += a; pz += b; }
-        }
-        __syncthreads();                                  // s_sum / s_nz of the previous sweep have been read
-        if (lane == 31) { s_sum[warp] = ps; s_nz[warp] = pz; }
-        __syncthreads();
-        if (warp == 0) {
-            int64_t a = s_sum[lane];
-            int32_t b = s_nz[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t a2 = __shfl_up_sync(0xffffffffu, a, o);
-                const int32_t b2 = __shfl_up_sync(0xffffffffu, b, o);
-                if (lane >= o) { a += a2; b += b2; }
-            }
-            s_sum[lane] = a;
-            s_nz[lane] = b;
-        }
-        __syncthreads();
+        block_scan_pair(ps, pz, lane, warp, s_sum, s_nz);
         int64_t excl = carry_sum + (warp ? s_sum[warp - 1] : 0) + ps - tsum;
         int32_t rank = carry_nz + (warp ? s_nz[warp - 1] : 0) + pz - tnz;
 #pragma unroll
         for (int k = 0; k < kScanI; ++k) {
             const int64_t i = i0 + k;
-            if (i < n) {
+            if (i < hi) {
                 if (first) first[i] = (int32_t)excl;
                 if (info2) { info2[2 * i] = (int32_t)excl; info2[2 * i + 1] = c[k]; }
                 if (c[k] > 0) {
@@ -88,7 +130,6 @@ k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int32_t *__restrict
         carry_sum += s_sum[31];
         carry_nz += s_nz[31];
     }
-    if (tid == 0) { totals[0] = carry_sum; totals[1] = carry_nz; }
 }
 
 // ------------------------------------------------------------------------------------------------ merge with payloads
@@ -252,7 +293,7 @@ k_ray_test_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays
                 od = fmaxf(od, fabsf(rays_o[i * 3 + d] - rays_o[(i - 1) * 3 + d]) / a.r[d]);
             }
             const float len = fmaxf(fmaxf(fabsf(rays_d[i * 3]), fabsf(rays_d[i * 3 + 1])), fabsf(rays_d[i * 3 + 2]));
-            close += (dd <= 0.01f * len && od <= 0.01f) ? 1u : 0u;
+            close += (dd <= 0.03f * len && od <= 0.03f) ? 1u : 0u;
         }
         float tn = 0.f, tf = 0.f;
 #pragma unroll
@@ -299,12 +340,20 @@ k_gather_rays(const int64_t *__restrict__ idx, int64_t n, const float *__restric
 using namespace nsb;
 #define STREAM ((cudaStream_t)stream)
 
+extern "C" int64_t nsb_scan_workspace_bytes(void) { return (int64_t)sizeof(ScanWs); }
+
 extern "C" int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first, int32_t *info2, int64_t *nz_index, int64_t *nz_pack,
-                               const int64_t *src, int64_t *nz_src, int64_t *totals, void *stream) {
-    NSB_REQUIRE(totals, "nsb_scan_counts: totals is NULL");
+                               const int64_t *src, int64_t *nz_src, int64_t *totals, void *workspace_zeroed, void *stream) {
+    NSB_REQUIRE(totals && workspace_zeroed, "nsb_scan_counts: totals / workspace is NULL");
     NSB_REQUIRE(n == 0 || counts, "nsb_scan_counts: counts is NULL");
     NSB_REQUIRE(!nz_src || src, "nsb_scan_counts: nz_src needs src");
-    k_scan_counts<<<1, kScanT, 0, STREAM>>>(counts, n, first, info2, nz_index, nz_pack, src, nz_src, totals);
+    int64_t nb = (n + (int64_t)kScanT * kScanI - 1) / ((int64_t)kScanT * kScanI);
+    const int64_t cap = sm_count() < kScanMaxBlocks ? sm_count() : kScanMaxBlocks;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    int64_t seg = (n + nb - 1) / nb;
+    seg = (seg + kScanI - 1) / kScanI * kScanI;
+    k_scan_counts<<<(unsigned)nb, kScanT, 0, STREAM>>>(counts, n, seg, (ScanWs *)workspace_zeroed, first, info2, nz_index, nz_pack, src, nz_src, totals);
     return check_launch("nsb_scan_counts");
 }
 

@@ -109,6 +109,16 @@ class _GatherUnique(torch.autograd.Function):
         return d, None, None
 
 
+_SCAN_WS = []
+
+
+def _scan_ws_bytes():
+    if not _SCAN_WS:
+        L.lib().nsb_scan_workspace_bytes.restype = ctypes.c_int64
+        _SCAN_WS.append(int(L.lib().nsb_scan_workspace_bytes()))
+    return _SCAN_WS[0]
+
+
 @torch.no_grad()
 def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False, want_pack=False, src=None, totals=None):
     """One launch + ONE host read: exclusive scan of int32 counts and compaction of the non-zero entries.
@@ -121,9 +131,10 @@ def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False,
     nz_src = torch.empty(n, dtype=torch.int64, device=dev) if src is not None else None
     if totals is None:               # else: a caller-owned int64[>=2] whose further slots another kernel filled; read in the same sync
         totals = torch.empty(2, dtype=torch.int64, device=dev)
+    ws = torch.zeros(_scan_ws_bytes(), dtype=torch.uint8, device=dev)
     L.check(L.lib().nsb_scan_counts(L.ptr(counts, "i32"), L.c_i64(n), L.ptr(first, allow_none=True), L.ptr(info2, allow_none=True),
                                     L.ptr(index, allow_none=True), L.ptr(pack, allow_none=True), L.ptr(src, "i64", allow_none=True),
-                                    L.ptr(nz_src, allow_none=True), L.ptr(totals), L.stream_ptr()), "scan_counts")
+                                    L.ptr(nz_src, allow_none=True), L.ptr(totals), L.ptr(ws), L.stream_ptr()), "scan_counts")
     host = totals.tolist()                            # the one host sync: output sizes are data dependent
     total, nnz = host[0], host[1]
     out = dict(total=int(total), n_nonzero=int(nnz), first=first, info2=info2, extra=host[2:])

@@ -54,8 +54,9 @@ def run_packs(tag):
 
 
 ref = None
-for variant, name in ((0, "libm softplus + cell addressing"), (1, "sfu softplus + cell addressing")):
-    for ctas in (8, 6, 4, 3):
+for variant, name in ((2, "libm softplus, 1 level/trip"), (0, "libm softplus, 2 levels/trip"), (3, "sfu softplus, 1 level/trip"),
+                      (1, "sfu softplus, 2 levels/trip")):
+    for ctas in (7, 6, 5):
         os.environ["NSB_SDF_VARIANT"], os.environ["NSB_SDF_CTAS"] = str(variant), str(ctas)
         s = run(f"{name}, {ctas} CTA/SM")
         s2 = run_packs(f"{name}, {ctas} CTA/SM, RAY-TILED")
@@ -66,7 +67,7 @@ for variant, name in ((0, "libm softplus + cell addressing"), (1, "sfu softplus 
             dd = (s - ref).abs()
             print(f"    vs variant 0: max |d| {float(dd.max()):.3e}, differing {float((dd > 0).float().mean()) * 100:.3f} %", flush=True)
 # point order: the same points, pixel-patch-major (8x4 pixel tiles x 65 depths) instead of ray-major
-os.environ["NSB_SDF_VARIANT"], os.environ["NSB_SDF_CTAS"] = "0", "6"
+os.environ["NSB_SDF_VARIANT"], os.environ["NSB_SDF_CTAS"] = "2", "6"
 perm = torch.randperm(t.numel(), device=dev)
 ridx_r, t_r = ridx[perm].contiguous(), t[perm].contiguous()
 ridx, t = ridx_r, t_r
