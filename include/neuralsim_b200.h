@@ -102,6 +102,13 @@ int nsb_ray_marching(int64_t n_rays, const float *rays_o, const float *rays_d, c
                      int32_t rz, const uint8_t *grid_binary, float step_size, float max_step_size,
                      float dt_gamma, uint32_t max_steps, const int32_t *packed_info, int32_t *num_steps,
                      float *t_starts, float *t_ends, int32_t *ridx, int32_t *gidx, int32_t *bidx, void *stream);
+/* The same with the second round restricted to the rays ray_list[0..n_list) (those whose first-round count is non-zero: on an
+ * image ~10 % of the rays); ray_list == NULL marches all n_rays.  t_ends / gidx / bidx may be NULL in the second round. */
+int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
+                            const float *roi, const int32_t *batch_inds, int32_t rx, int32_t ry, int32_t rz,
+                            const uint8_t *grid_binary, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                            const int32_t *packed_info, int32_t *num_steps, float *t_starts, float *t_ends, int32_t *ridx,
+                            int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * _pack_ops  (csrc/pack_ops/pack_ops.cpp:20-58, pack_ops.h:11-65).  fp32 features unless noted.
@@ -241,9 +248,11 @@ int nsb_merge_sorted_vals(const float *dep_a, const float *sdf_a, const int64_t 
                           int64_t n_packs, int32_t n_b, float *dep_m, float *sdf_m, int64_t *pack_infos_m, void *stream);
 /* sort(cat(fine stages)) + merge_two_batch_a_includes_b with the coarse samples + ray ids + interval mid-points
  * (neus_ray_query.py:907-976): coarse[n_rays, n_coarse] sorted rows; fine[n_hit, n_fine] rows of the rays ridx_hit (sorted,
- * unique).  -> d1, mid [S], ridx_all [S], pack_infos [n_rays, 2], S = n_rays n_coarse + n_hit n_fine. */
+ * unique), each a concatenation of n_runs sorted runs of run_len_host[q] samples (one per up-sampling stage; HOST array, <= 8 runs).
+ * -> d1, mid [S], ridx_all [S], pack_infos [n_rays, 2], S = n_rays n_coarse + n_hit n_fine. */
 int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_t n_coarse, const int64_t *ridx_hit, int64_t n_hit, const float *fine,
-                          int32_t n_fine, float *d1, float *mid, int64_t *ridx_all, int64_t *pack_infos, void *stream);
+                          int32_t n_fine, const int32_t *run_len_host, int32_t n_runs, float *d1, float *mid, int64_t *ridx_all,
+                          int64_t *pack_infos, void *stream);
 /* gather of the samples packed_volume_render_compression keeps (pack_ops.py:286-291): slot = first_out[p] + rank inside the pack. */
 int nsb_compact_samples(const uint8_t *selector, const int64_t *pack_infos, const int32_t *first_out, const int32_t *kept, int64_t n_packs,
                         const int64_t *ridx_all, const float *t, const float *alpha, int64_t *pidx, int64_t *ridx_c, float *t_c,

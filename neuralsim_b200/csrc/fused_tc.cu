@@ -330,7 +330,7 @@ static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta 
     // ray-major order: libm softplus (its longer epilogue keeps fewer warps in the gather phase at once -> less L1 thrash);
     // ray-tiled order: SFU softplus (gathers coalesce, the kernel is issue-bound again).  profiles/r01e_ab.txt
     // variants: 0 libm / 2 levels per trip, 1 SFU / 2, 2 libm / 1, 3 SFU / 1
-    if (variant < 0) variant = (MODE == 2) ? 1 : 2;
+    if (variant < 0) variant = 1;                      // SFU softplus, two levels per trip: best in both orders (profiles/r01f_ab.txt)
     if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
     else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
     else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);

@@ -24,6 +24,8 @@ struct MarchArgs {
     int32_t *num_steps;
     float *t_starts, *t_ends;
     int32_t *ridx, *gidx, *bidx;
+    const int64_t *ray_list;       // second round only: the rays to re-march (those with samples); NULL = all n_rays
+    int64_t n_list;
 };
 
 __device__ __forceinline__ float calc_dt(float t, float dt_gamma, float dt_min, float dt_max) {
@@ -60,7 +62,9 @@ __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
     }
     const bool first_round = (a.packed_info == nullptr);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_rays; i += stride) {
+    const int64_t n_work = a.ray_list ? a.n_list : a.n_rays;
+    for (int64_t j_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j_ < n_work; j_ += stride) {
+        const int64_t i = a.ray_list ? a.ray_list[j_] : j_;
         int b = 0;
         if (a.batch_inds) {
             b = a.batch_inds[i];
@@ -142,18 +146,27 @@ extern "C" int nsb_ray_marching(int64_t n_rays, const float *rays_o, const float
                                 int32_t rz, const uint8_t *grid_binary, float step_size, float max_step_size,
                                 float dt_gamma, uint32_t max_steps, const int32_t *packed_info, int32_t *num_steps,
                                 float *t_starts, float *t_ends, int32_t *ridx, int32_t *gidx, int32_t *bidx, void *stream) {
-    if (n_rays == 0) return 0;
+    return nsb_ray_marching_listed(n_rays, rays_o, rays_d, t_min, t_max, roi, batch_inds, rx, ry, rz, grid_binary, step_size, max_step_size, dt_gamma,
+                                   max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, nullptr, 0, stream);
+}
+
+extern "C" int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
+                                       const float *roi, const int32_t *batch_inds, int32_t rx, int32_t ry, int32_t rz,
+                                       const uint8_t *grid_binary, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                                       const int32_t *packed_info, int32_t *num_steps, float *t_starts, float *t_ends, int32_t *ridx,
+                                       int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, void *stream) {
+    if (n_rays == 0 || (ray_list && n_list == 0)) return 0;
     NSB_REQUIRE(rays_o && rays_d && t_min && t_max && roi && grid_binary, "nsb_ray_marching: NULL input");
     NSB_REQUIRE(rx > 0 && ry > 0 && rz > 0, "nsb_ray_marching: bad grid resolution");
-    if (packed_info == nullptr) NSB_REQUIRE(num_steps, "nsb_ray_marching: first round needs num_steps");
+    if (packed_info == nullptr) NSB_REQUIRE(num_steps && !ray_list, "nsb_ray_marching: first round needs num_steps (and marches every ray)");
     else NSB_REQUIRE(t_starts && ridx, "nsb_ray_marching: second round needs t_starts and ridx (t_ends / gidx / bidx are optional)");
     MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, batch_inds, rx, ry, rz, grid_binary, step_size, max_step_size,
-                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx};
+                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, ray_list, n_list};
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cells = (int64_t)rx * ry * rz;
     const size_t smem = (size_t)((cells + 31) / 32) * 4;
     const bool use_smem = (batch_inds == nullptr) && smem <= 96 * 1024;
-    const unsigned grid = wave_grid(n_rays, 256, 2);
+    const unsigned grid = wave_grid(ray_list ? n_list : n_rays, 256, 2);
     if (use_smem) {
         static bool attr_set = false;
         if (!attr_set) {

@@ -161,18 +161,20 @@ k_neus_alpha_bwd(const float *__restrict__ sdf, const int64_t *__restrict__ pi, 
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
         for (int64_t k = lane; k < n; k += 32) {
+            const float g_own = (k < n - 1) ? d_alpha[b + k] : 0.f, g_prev = (k > 0) ? d_alpha[b + k - 1] : 0.f;
+            if (g_own == 0.f && g_prev == 0.f) { d_sdf[b + k] = 0.f; continue; }     // most samples: compressed away / empty space
             const float s = sdf[b + k];
             const float c = sigmoidf_(s * inv_s);
             float gc = 0.f;                                             // dL/dc_k
             if (k < n - 1) {                                            // as c_i of interval k
                 const float c1 = sigmoidf_(sdf[b + k + 1] * inv_s);
                 const float den = c + 1e-5f;
-                if ((c - c1) / den >= 0.f) gc += d_alpha[b + k] * (c1 + 1e-5f) / (den * den);
+                if ((c - c1) / den >= 0.f) gc += g_own * (c1 + 1e-5f) / (den * den);
             }
             if (k > 0) {                                                // as c_{i+1} of interval k-1
                 const float cp = sigmoidf_(sdf[b + k - 1] * inv_s);
                 const float den = cp + 1e-5f;
-                if ((cp - c) / den >= 0.f) gc -= d_alpha[b + k - 1] / den;
+                if ((cp - c) / den >= 0.f) gc -= g_prev / den;
             }
             const float dc = c * (1.f - c);
             d_sdf[b + k] = gc * dc * inv_s;

@@ -178,11 +178,23 @@ k_merge_vals(const float *__restrict__ dep_a, const float *__restrict__ sdf_a, c
 // Ray r of the R tested rays carries nc coarse depths (sorted); if r == ridx_hit[j] it also carries the nf fine depths of
 // row j (a concatenation of sorted runs).  Output pack r = the sorted union; first_r = nc r + nf #{hit rays < r}.
 //   d1[first + k] = k-th smallest;  mid[first + k] = d1_k + (d1_{k+1} - d1_k) / 2 (last: + 0);  ridx_all = r.
-constexpr int kAsmWarps = 8;
+constexpr int kAsmWarps = 8, kAsmMaxRuns = 8;
+struct AsmRuns { int n, len[kAsmMaxRuns]; };              // the fine row is a concatenation of `n` sorted runs (one per up-sampling stage)
+
+__device__ __forceinline__ int count_less(const float *a, int n, float v, bool or_equal) {   // #{a_i < v} or #{a_i <= v}, a sorted
+    int lo = 0, cnt = n;
+    while (cnt > 0) {
+        const int step = cnt >> 1;
+        const float u = a[lo + step];
+        if (or_equal ? (u <= v) : (u < v)) { lo += step + 1; cnt -= step + 1; } else cnt = step;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(kAsmWarps * 32)
 k_assemble_boundary(const float *__restrict__ coarse, int64_t n_rays, int nc, const int64_t *__restrict__ ridx_hit, int64_t n_hit,
-                    const float *__restrict__ fine, int nf, float *__restrict__ d1, float *__restrict__ mid, int64_t *__restrict__ ridx_all,
-                    int64_t *__restrict__ pack_infos) {
+                    const float *__restrict__ fine, int nf, const AsmRuns runs, float *__restrict__ d1, float *__restrict__ mid,
+                    int64_t *__restrict__ ridx_all, int64_t *__restrict__ pack_infos) {
     extern __shared__ float s_v[];                        // [warps][2][nc + nf]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cap = nc + nf;
     float *raw = s_v + (size_t)w * 2 * cap, *srt = raw + cap;
@@ -195,25 +207,34 @@ k_assemble_boundary(const float *__restrict__ coarse, int64_t n_rays, int nc, co
         const bool hit = lo < n_hit && ridx_hit[lo] == r;
         const int n = nc + (hit ? nf : 0);
         const int64_t first = (int64_t)nc * r + (int64_t)nf * lo;
-        __syncwarp();
-        for (int k = lane; k < nc; k += 32) raw[k] = coarse[r * nc + k];
-        if (hit) for (int k = lane; k < nf; k += 32) raw[nc + k] = fine[lo * nf + k];
-        __syncwarp();
-        if (hit) {
-            for (int e = lane; e < n; e += 32) {          // stable rank by counting
-                const float v = raw[e];
-                int rank = 0;
-                for (int k = 0; k < n; ++k) {
-                    const float u = raw[k];
-                    rank += (u < v || (u == v && k < e)) ? 1 : 0;
-                }
-                srt[rank] = v;
+        if (lane == 0) { pack_infos[2 * r] = first; pack_infos[2 * r + 1] = n; }
+        if (!hit) {                                       // the coarse row is already sorted: straight copy
+            for (int k = lane; k < nc; k += 32) {
+                const float v = coarse[r * nc + k];
+                const float diff = (k < nc - 1) ? __fsub_rn(coarse[r * nc + k + 1], v) : 0.f;
+                d1[first + k] = v;
+                mid[first + k] = __fadd_rn(v, __fmul_rn(diff, 0.5f));
+                ridx_all[first + k] = r;
             }
-        } else {
-            for (int e = lane; e < n; e += 32) srt[e] = raw[e];
+            continue;
         }
         __syncwarp();
-        if (lane == 0) { pack_infos[2 * r] = first; pack_infos[2 * r + 1] = n; }
+        for (int k = lane; k < nc; k += 32) raw[k] = coarse[r * nc + k];
+        for (int k = lane; k < nf; k += 32) raw[nc + k] = fine[lo * nf + k];
+        __syncwarp();
+        // stable rank of every element among the 1 + runs.n sorted runs: own index + (<=-count in earlier runs) + (<-count in later runs)
+        for (int e = lane; e < n; e += 32) {
+            const float v = raw[e];
+            int rank = 0, start = 0;
+            for (int q = -1; q < runs.n; ++q) {
+                const int len = q < 0 ? nc : runs.len[q];
+                if (e >= start && e < start + len) rank += e - start;
+                else rank += count_less(raw + start, len, v, /*or_equal=*/start < e);
+                start += len;
+            }
+            srt[rank] = v;
+        }
+        __syncwarp();
         for (int k = lane; k < n; k += 32) {
             const float v = srt[k];
             const float diff = (k < n - 1) ? __fsub_rn(srt[k + 1], v) : 0.f;
@@ -370,7 +391,8 @@ extern "C" int nsb_merge_sorted_vals(const float *dep_a, const float *sdf_a, con
 }
 
 extern "C" int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_t n_coarse, const int64_t *ridx_hit, int64_t n_hit, const float *fine,
-                                     int32_t n_fine, float *d1, float *mid, int64_t *ridx_all, int64_t *pack_infos, void *stream) {
+                                     int32_t n_fine, const int32_t *run_len, int32_t n_runs, float *d1, float *mid, int64_t *ridx_all,
+                                     int64_t *pack_infos, void *stream) {
     if (n_rays == 0) return 0;
     NSB_REQUIRE(coarse && d1 && mid && ridx_all && pack_infos, "nsb_assemble_boundary: NULL argument");
     NSB_REQUIRE(n_hit == 0 || (ridx_hit && fine), "nsb_assemble_boundary: hit rays need ridx_hit and fine");
@@ -379,8 +401,14 @@ extern "C" int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_assemble_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
     NSB_REQUIRE(smem <= 96 * 1024, "nsb_assemble_boundary: too many samples per ray for shared memory");
+    AsmRuns runs{};
+    NSB_REQUIRE(n_runs >= 0 && n_runs <= kAsmMaxRuns && (n_runs == 0 || run_len), "nsb_assemble_boundary: at most %d sorted runs", kAsmMaxRuns);
+    int tot = 0;
+    for (int q = 0; q < n_runs; ++q) { runs.len[q] = run_len[q]; tot += run_len[q]; }
+    runs.n = n_runs;
+    NSB_REQUIRE(tot == n_fine, "nsb_assemble_boundary: run lengths must add up to n_fine");
     k_assemble_boundary<<<wave_grid(n_rays * 32, kAsmWarps * 32, 8), kAsmWarps * 32, smem, STREAM>>>(coarse, n_rays, n_coarse, ridx_hit, n_hit, fine, n_fine,
-                                                                                                  d1, mid, ridx_all, pack_infos);
+                                                                                                  runs, d1, mid, ridx_all, pack_infos);
     return check_launch("nsb_assemble_boundary");
 }
 

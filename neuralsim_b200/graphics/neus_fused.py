@@ -159,17 +159,20 @@ def merge_sorted_vals(dep_a, sdf_a, pack_infos_a, dep_b, sdf_b):
 
 
 @torch.no_grad()
-def assemble_boundary(coarse, ridx_hit, fine):
-    """coarse [R, nc] (sorted rows), fine [n_hit, nf] rows of rays ridx_hit -> (d1 [S], mid [S], ridx_all [S], pack_infos [R,2])."""
+def assemble_boundary(coarse, ridx_hit, fine, run_len=None):
+    """coarse [R, nc] (sorted rows), fine [n_hit, nf] rows of rays ridx_hit, every row a concatenation of sorted runs of `run_len`
+    samples (default: one run) -> (d1 [S], mid [S], ridx_all [S], pack_infos [R,2])."""
     R, nc = coarse.shape
     n_hit, nf = (fine.shape if fine is not None else (0, 0))
     S, dev = R * nc + n_hit * nf, coarse.device
     d1, mid = torch.empty(S, dtype=torch.float32, device=dev), torch.empty(S, dtype=torch.float32, device=dev)
     ridx_all = torch.empty(S, dtype=torch.int64, device=dev)
     pi = torch.empty(R, 2, dtype=torch.int64, device=dev)
+    run_len = [nf] if run_len is None else list(run_len)
+    rl = (ctypes.c_int32 * len(run_len))(*run_len)
     L.check(L.lib().nsb_assemble_boundary(L.ptr(coarse, "f32"), L.c_i64(R), L.c_i32(nc), L.ptr(ridx_hit, "i64", allow_none=True), L.c_i64(n_hit),
-                                          L.ptr(fine, "f32", allow_none=True), L.c_i32(nf), L.ptr(d1), L.ptr(mid), L.ptr(ridx_all), L.ptr(pi),
-                                          L.stream_ptr()), "assemble_boundary")
+                                          L.ptr(fine, "f32", allow_none=True), L.c_i32(nf), rl, L.c_i32(len(run_len)), L.ptr(d1), L.ptr(mid),
+                                          L.ptr(ridx_all), L.ptr(pi), L.stream_ptr()), "assemble_boundary")
     return d1, mid, ridx_all, pi
 
 
@@ -217,7 +220,8 @@ def march_lean(occ_grid, rays_o, rays_d, near, far, *, step_size, max_steps, max
     t_starts = torch.empty(M, dtype=torch.float32, device=dev)
     ridx = torch.empty(M, dtype=torch.int32, device=dev)
     with L.KERNEL_TIMER.time("march", R):
-        L.check(L.lib().nsb_ray_marching(*args, L.ptr(sc["info2"]), None, L.ptr(t_starts), None, L.ptr(ridx), None, None, L.stream_ptr()), "ray_marching")
+        L.check(L.lib().nsb_ray_marching_listed(*args, L.ptr(sc["info2"]), None, L.ptr(t_starts), None, L.ptr(ridx), None, None,
+                                                L.ptr(sc["index"], "i64"), L.c_i64(sc["n_nonzero"]), L.stream_ptr()), "ray_marching")
     return sc["index"], sc["pack"], t_starts, ridx.long()
 
 

@@ -22,6 +22,10 @@ if [ "${3:-}" = "ab" ]; then
   cat gpurun_out/${TAG}_ab.txt
   exit 0
 fi
+if [ "${3:-}" = "abs" ]; then
+  timeout 600 python profiles/ab_scatter.py > gpurun_out/${TAG}_ab_scatter.txt 2>&1
+  cat gpurun_out/${TAG}_ab_scatter.txt
+fi
 # one --set full capture of every hot kernel of ONE step (the 8 big launches of the first step)
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_fused_sdf_tc|k_sdf_bwd_tc|k_color_' -c 8 -f -o gpurun_out/${TAG}_hot \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ref-cuda > gpurun_out/${TAG}_ncu_hot.log 2>&1

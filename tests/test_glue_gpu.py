@@ -72,9 +72,11 @@ def test_assemble_boundary_equals_reference_chain():
     r_ref[pidx0], r_ref[pidx1] = ridx_c.unsqueeze(-1), ridx_hit.unsqueeze(-1)
     d_ref[pidx0], d_ref[pidx1] = coarse, depths_1
     mid_ref = d_ref + packed_diff(d_ref, pi_ref) / 2.
-    d1, mid, ridx_all, pi = NF.assemble_boundary(coarse, ridx_hit, fine_all)
+    d1, mid, ridx_all, pi = NF.assemble_boundary(coarse, ridx_hit, fine_all, run_len=[9, 9, 33])
     assert torch.equal(pi, pi_ref) and torch.equal(d1, d_ref) and torch.equal(ridx_all, r_ref) and torch.equal(mid, mid_ref)
     # no ray carries fine samples
+    d1s, _, _, _ = NF.assemble_boundary(coarse, ridx_hit, depths_1)            # one sorted run per row
+    assert torch.equal(d1s, d_ref)
     d1, mid, ridx_all, pi = NF.assemble_boundary(coarse, ridx_hit[:0], fine_all[:0])
     assert torch.equal(d1, coarse.flatten()) and torch.equal(pi[:, 1], torch.full((R,), nc, device="cuda"))
 
