@@ -117,35 +117,73 @@ def loss_of(rendered):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons DURING the timed region.  Sampled in-process through NVML (pynvml): forking `nvidia-smi` from a
+    thread of this (large) process stalls the main thread for tens of ms -- on a 23 ms step that showed up as 2x slower steps."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index=0):
         self.samples, self.reasons, self.max_mhz, self._stop, self.index = [], set(), None, threading.Event(), index
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
-                    if "Active" in v and "Not" not in v:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __enter__(self):
-        self.t.start(); return self
+        if self.nv is not None:
+            self.t.start()
+        else:                                  # no NVML binding: ONE looping nvidia-smi, forked here (before the timed region), read afterwards
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.proc = None
+        return self
 
     def __exit__(self, *a):
-        self._stop.set(); self.t.join(timeout=6)
+        self._stop.set()
+        if self.nv is not None:
+            self.t.join(timeout=2)
+        elif getattr(self, "proc", None) is not None:
+            self.proc.terminate()
+            try:
+                out = self.proc.communicate(timeout=5)[0]
+            except Exception:
+                out = ""
+            for line in out.strip().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    self.samples.append(float(f[0])); self.max_mhz = float(f[1])
+                except Exception:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(name)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["NVML unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline / reference arm

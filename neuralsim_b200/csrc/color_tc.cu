@@ -722,29 +722,34 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
                 const uint32_t p = g4 * 4 + q;
-                if (valid && (int)m.level[p] <= max_level) {
-                    uint32_t cell[8];
-                    float w[8], fr[3], sc[3];
-                    level_cells3(m, p, xs, cell, w, fr, sc);
-                    float2 *gp = level_grad_ptr(m, p, d_grid);
-                    const float g0 = r16f(gg[2 * q]), g1 = r16f(gg[2 * q + 1]);
-                    const float h0 = hz[2 * q], h1 = hz[2 * q + 1];
+                if ((int)m.level[p] > max_level) continue;               // uniform
+                uint32_t cell[8];
+                float w[8], fr[3], sc[3], ua[8], ub[8];
+                level_cells3(m, p, xs, cell, w, fr, sc);
+                const float g0 = valid ? r16f(gg[2 * q]) : 0.f, g1 = valid ? r16f(gg[2 * q + 1]) : 0.f;
+                const float h0 = valid ? hz[2 * q] : 0.f, h1 = valid ? hz[2 * q + 1] : 0.f;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float wsum = 0.f;
+                for (int c = 0; c < 8; ++c) {
+                    float wsum = 0.f;
 #pragma unroll
-                        for (int gd = 0; gd < 3; ++gd) {
-                            float ww = __fmul_rn(sc[gd], gin[gd]);
+                    for (int gd = 0; gd < 3; ++gd) {
+                        float ww = __fmul_rn(sc[gd], gin[gd]);
 #pragma unroll
-                            for (int d = 0; d < 3; ++d) {
-                                if (d == gd) continue;
-                                ww = __fmul_rn(ww, (c & (1 << d)) ? fr[d] : __fsub_rn(1.f, fr[d]));
-                            }
-                            wsum += (c & (1 << gd)) ? ww : -ww;
+                        for (int d = 0; d < 3; ++d) {
+                            if (d == gd) continue;
+                            ww = __fmul_rn(ww, (c & (1 << d)) ? fr[d] : __fsub_rn(1.f, fr[d]));
                         }
-                        const float a = g0 * wsum + h0 * w[c], b = g1 * wsum + h1 * w[c];
-                        red_add2(gp + cell[c], a, b);
+                        wsum += (c & (1 << gd)) ? ww : -ww;
                     }
+                    ua[c] = g0 * wsum + h0 * w[c];
+                    ub[c] = g1 * wsum + h1 * w[c];
+                }
+                bool issue = valid;
+                if (level_mergeable(m, p)) issue = warp_merge_updates(cell_key3(m, p, xs), valid, ua, ub, lane);   // neighbouring samples, same cell
+                if (issue) {
+                    float2 *gp = level_grad_ptr(m, p, d_grid);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add2(gp + cell[c], ua[c], ub[c]);
                 }
             }
         }

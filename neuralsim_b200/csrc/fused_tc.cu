@@ -277,14 +277,19 @@ k_sdf_bwd_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
                 const uint32_t p = g4 * 4 + q;
-                if (active && (int)m.level[p] <= max_level) {
-                    uint32_t cell[8];
-                    float w[8];
-                    level_cells3(m, p, xs, cell, w);
-                    float2 *gp = level_grad_ptr(m, p, d_grid);
-                    const float g0 = dh[2 * q], g1 = dh[2 * q + 1];
+                if ((int)m.level[p] > max_level) continue;               // uniform
+                uint32_t cell[8];
+                float w[8], a[8], b[8];
+                level_cells3(m, p, xs, cell, w);
+                const float g0 = active ? dh[2 * q] : 0.f, g1 = active ? dh[2 * q + 1] : 0.f;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) red_add2(gp + cell[c], g0 * w[c], g1 * w[c]);
+                for (int c = 0; c < 8; ++c) { a[c] = g0 * w[c]; b[c] = g1 * w[c]; }
+                bool issue = active;
+                if (level_mergeable(m, p)) issue = warp_merge_updates(cell_key3(m, p, xs), active, a, b, lane);   // neighbouring samples, same cell
+                if (issue) {
+                    float2 *gp = level_grad_ptr(m, p, d_grid);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add2(gp + cell[c], a[c], b[c]);
                 }
             }
         }

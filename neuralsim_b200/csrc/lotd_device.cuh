@@ -227,6 +227,47 @@ __device__ __forceinline__ void red_add2(float2 *dst, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(a), "f"(b) : "memory");
 }
 
+// ---- warp-merged table-gradient updates.  Measured (profiles/r01g_ab_scatter.txt): the fp32 atomics themselves bound the table
+// backward (80 G corner-updates/s whether the points are ordered or shuffled, at any occupancy), so the lever is FEWER atomics.
+// The lanes of a warp are consecutive samples of a ray; on the coarse / middle levels neighbouring samples fall into the same cell
+// and update the same 8 corners.  Runs of lanes with equal integer cell coordinates are summed with shuffles (segmented reduction
+// over contiguous runs; the run structure is one ballot) and only the run's first lane issues the 8 reductions.
+// `key` must identify the cell exactly (not its hash); lanes that carry no gradient pass active = false.
+__device__ __forceinline__ uint32_t cell_key3(const PLMeta &m, uint32_t p, const float (&xs)[3]) {      // res <= 1024 per axis
+    uint32_t k = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float v = __fmaf_rn(xs[d], (float)(m.res[p][d] - 2u), 0.5f);
+        k |= (__float_as_uint(__fadd_rd(v, 8388608.f)) - 0x4B000000u) << (10 * d);
+    }
+    return k;
+}
+__device__ __forceinline__ bool level_mergeable(const PLMeta &m, uint32_t p) {
+    return m.res[p][0] <= 1024u && m.res[p][1] <= 1024u && m.res[p][2] <= 1024u;
+}
+
+// a[c], b[c]: this lane's updates of corner c (feature 0 / 1).  On return the lanes for which the result is true hold the sums of
+// their run and must issue them; the others are done.  Every lane of the warp must call (shuffles).
+__device__ __forceinline__ bool warp_merge_updates(uint32_t key, bool active, float (&a)[8], float (&b)[8], int lane) {
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    const bool prev_act = lane > 0 && ((act >> (lane - 1)) & 1u);
+    const bool head = !active || !prev_act || key != prev;       // inactive lanes are runs of their own
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    if (__popc(heads) > 24) return active;                       // (warp-uniform) little to merge: everyone issues its own
+    const uint32_t after = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));   // bit j: lane + 1 + j starts a new run
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool take = (lane + o < 32) && ((after & ((1u << o) - 1u)) == 0u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float av = __shfl_down_sync(0xffffffffu, a[c], o), bv = __shfl_down_sync(0xffffffffu, b[c], o);
+            if (take) { a[c] += av; b[c] += bv; }
+        }
+    }
+    return active && head;
+}
+
 // true when every pseudo level is a 2-feature level stored at an even element offset (the fast path's precondition)
 inline bool plmeta_two_feature_cells(const PLMeta &m) {
     for (uint32_t p = 0; p < m.n_pseudo; ++p)

@@ -63,6 +63,9 @@ def test_assemble_boundary_equals_reference_chain():
     ridx_hit = torch.randperm(R, generator=g)[:260].sort().values.cuda()
     stages = [(coarse[ridx_hit, :1] + torch.rand(260, n, generator=g).sort(-1).values.cuda() * 1.5) for n in (9, 9, 33)]
     stages[0][:, 0] = coarse[ridx_hit, 7]                  # a fine sample equal to a coarse one
+    stages[0] = stages[0].sort(-1).values                  # (every stage's row stays a sorted run)
+    stages[1][:, 3] = stages[0][:, 2]                      # equal samples in two stages
+    stages[1] = stages[1].sort(-1).values
     fine_all = torch.cat(stages, -1).contiguous()
     depths_1 = fine_all.sort(-1).values
     ridx_c = torch.arange(R, device="cuda")
