@@ -265,9 +265,10 @@ int nsb_scatter_f32(const float *src, const int64_t *idx, int64_t n, float *dst,
 int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64_t n, const float *center3, const float *radius3, int has_near,
                       float near_clip, int has_far, float far_clip, float *o_n, float *d_n, float *near, float *far, int32_t *flag,
                       int64_t *coherent_pairs, void *stream);
-/* rows idx[j] of (o_n, d_n, near, far) -> row j of the compacted outputs. */
+/* rows idx[j] of (o_n, d_n, near, far) and of one optional per-ray fp32 payload extra[., extra_cols] (rays_h_appear) -> row j of
+ * the compacted outputs. */
 int nsb_gather_rays(const int64_t *idx, int64_t n, const float *o_n, const float *d_n, const float *near, const float *far, float *o_c,
-                    float *d_c, float *near_c, float *far_c, void *stream);
+                    float *d_c, float *near_c, float *far_c, const float *extra, float *extra_c, int32_t extra_cols, void *stream);
 
 /* ---------------------------------------------------------------- fused colour / normal query (csrc/color_tc.cu)
  * The whole LoTDNeuS.forward of the reference for packed samples (nr3d_lib/models/fields/neus/lotd_neus.py:141-167 =

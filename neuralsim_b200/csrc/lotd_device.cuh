@@ -203,11 +203,17 @@ __device__ __forceinline__ void level_cells3(const PLMeta &m, uint32_t p, const 
 }
 
 // fp16 table viewed as 32-bit cells of level p / fp32 gradient viewed as float2 cells of level p
+// (the empty asm keeps the level pointer in an ordinary 64-bit register: `pointer + cell` is then ONE IMAD.WIDE with an immediate
+//  stride; with the pointer in a uniform register ptxas needs an extra MOV per corner for the stride)
 __device__ __forceinline__ const uint32_t *level_cells_ptr(const PLMeta &m, uint32_t p, const __half *grid) {
-    return reinterpret_cast<const uint32_t *>(grid + m.base[p]);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(grid + m.base[p]);
+    asm volatile("" : "+l"(q));
+    return q;
 }
 __device__ __forceinline__ float2 *level_grad_ptr(const PLMeta &m, uint32_t p, float *d_grid) {
-    return reinterpret_cast<float2 *>(d_grid + m.base[p]);
+    float2 *q = reinterpret_cast<float2 *>(d_grid + m.base[p]);
+    asm volatile("" : "+l"(q));
+    return q;
 }
 
 __device__ __forceinline__ uint32_t level_feat2_cells(const uint32_t *__restrict__ lp, const uint32_t (&cell)[8], const float (&w)[8]) {

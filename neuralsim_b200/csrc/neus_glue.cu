@@ -345,7 +345,8 @@ k_ray_test_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays
 // compaction of the rays that passed: row j of every output = row idx[j] of the inputs
 __global__ void __launch_bounds__(256)
 k_gather_rays(const int64_t *__restrict__ idx, int64_t n, const float *__restrict__ o_n, const float *__restrict__ d_n, const float *__restrict__ near,
-              const float *__restrict__ far, float *__restrict__ o_c, float *__restrict__ d_c, float *__restrict__ near_c, float *__restrict__ far_c) {
+              const float *__restrict__ far, float *__restrict__ o_c, float *__restrict__ d_c, float *__restrict__ near_c, float *__restrict__ far_c,
+              const float *__restrict__ extra, float *__restrict__ extra_c, int extra_cols) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         const int64_t i = idx[j];
@@ -353,6 +354,7 @@ k_gather_rays(const int64_t *__restrict__ idx, int64_t n, const float *__restric
         for (int d = 0; d < 3; ++d) { o_c[j * 3 + d] = o_n[i * 3 + d]; d_c[j * 3 + d] = d_n[i * 3 + d]; }
         near_c[j] = near[i];
         far_c[j] = far[i];
+        for (int c = 0; c < extra_cols; ++c) extra_c[j * extra_cols + c] = extra[i * extra_cols + c];     // per-ray payload (h_appear)
     }
 }
 
@@ -441,9 +443,10 @@ extern "C" int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64
 }
 
 extern "C" int nsb_gather_rays(const int64_t *idx, int64_t n, const float *o_n, const float *d_n, const float *near, const float *far, float *o_c,
-                               float *d_c, float *near_c, float *far_c, void *stream) {
+                               float *d_c, float *near_c, float *far_c, const float *extra, float *extra_c, int32_t extra_cols, void *stream) {
     if (n == 0) return 0;
     NSB_REQUIRE(idx && o_n && d_n && near && far && o_c && d_c && near_c && far_c, "nsb_gather_rays: NULL argument");
-    k_gather_rays<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(idx, n, o_n, d_n, near, far, o_c, d_c, near_c, far_c);
+    NSB_REQUIRE(extra_cols == 0 || (extra && extra_c), "nsb_gather_rays: extra payload needs both pointers");
+    k_gather_rays<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(idx, n, o_n, d_n, near, far, o_c, d_c, near_c, far_c, extra, extra_c, extra_cols);
     return check_launch("nsb_gather_rays");
 }

@@ -86,10 +86,16 @@ class AABBSpace(nn.Module):
         n, ridx = sc["n_nonzero"], sc["index"]
         o_c, d_c = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
         n_c, f_c = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        # one per-ray fp32 payload (rays_h_appear) rides along in the gather kernel; anything else is indexed by torch
+        fused_key = next((k for k, v in extra_ray_data.items() if isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 and v.dim() == 2
+                          and v.shape[0] == R and v.is_contiguous() and not v.requires_grad), None)
+        ex = extra_ray_data[fused_key] if fused_key is not None else None
+        ex_c = torch.empty(n, ex.shape[1], device=dev) if ex is not None else None
         L.check(L.lib().nsb_gather_rays(L.ptr(ridx, "i64"), L.c_i64(n), L.ptr(o_n), L.ptr(d_n), L.ptr(nr), L.ptr(fr), L.ptr(o_c), L.ptr(d_c),
-                                        L.ptr(n_c), L.ptr(f_c), L.stream_ptr()), "gather_rays")
+                                        L.ptr(n_c), L.ptr(f_c), L.ptr(ex, allow_none=True), L.ptr(ex_c, allow_none=True),
+                                        L.c_i32(0 if ex is None else ex.shape[1]), L.stream_ptr()), "gather_rays")
         ret = dict(num_rays=n, rays_inds=ridx, near=n_c, far=f_c)
-        ret.update({k: (v[ridx] if isinstance(v, torch.Tensor) else v) for k, v in extra_ray_data.items()})
+        ret.update({k: (ex_c if k == fused_key else (v[ridx] if isinstance(v, torch.Tensor) else v)) for k, v in extra_ray_data.items()})
         ret.update(rays_o=o_c, rays_d=d_c)
         # image-ordered rays (>= 3/4 of the rays neighbour their predecessor): the queries traverse samples ray-tiled (csrc/fused_tc.cu)
         ret["rays_coherent"] = R > 64 and sc["extra"][0] >= 0.75 * (R - 1)
