@@ -26,9 +26,6 @@ import sys
 import threading
 import time
 
-# per-view tensor sizes differ (data-dependent sample counts): let the caching allocator grow segments instead of cudaMalloc-ing new ones
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
-
 import numpy as np
 import torch
 
@@ -120,76 +117,71 @@ def loss_of(rendered):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region.  Sampled in-process through NVML (pynvml): forking `nvidia-smi` from a
-    thread of this (large) process stalls the main thread for tens of ms -- on a 23 ms step that showed up as 2x slower steps."""
-    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+    """SM clock + throttle reasons DURING the timed region: ONE looping `nvidia-smi -lms 100` (the recipe of B200_PROFILING.md), forked
+    before the warm-up and read after the timed loops -- nothing is forked or queried from this process while the clock runs.
+    (An in-process NVML poll every 25 ms, and a thread forking nvidia-smi, both stalled the CUDA driver: 15 ms steps measured 50-230 ms.)
+    Samples are attributed to the timed region by nvidia-smi's own timestamps."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.samples, self.reasons, self.max_mhz, self._stop, self.index = [], set(), None, threading.Event(), index
-        self.armed = False
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.nv = self.h = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
-            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-        except Exception:
-            self.nv = None
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
+        self.samples, self.reasons, self.max_mhz, self.n_all = [], set(), None, 0
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                if self.armed:
-                    self.samples.append(mhz)
-                    for name, bit in self.REASONS:
-                        if mask & bit:
-                            self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.025)
+    @property
+    def armed(self):
+        return self.t0 is not None and self.t1 is None
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    @armed.setter
+    def armed(self, on):
+        if on:
+            self.t0, self.t1 = time.time(), None
+        else:
+            self.t1 = time.time()
 
     def __enter__(self):
-        if self.nv is not None:
-            self.t.start()
-        else:                                  # no NVML binding: ONE looping nvidia-smi, forked here (before the timed region), read afterwards
-            try:
-                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
-                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            except Exception:
-                self.proc = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = vis.split(",")[self.index].strip() if vis and len(vis.split(",")) > self.index else str(self.index)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", phys],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        if self.nv is not None:
-            self.t.join(timeout=2)
-        elif getattr(self, "proc", None) is not None:
-            self.proc.terminate()
+        if self.proc is None:
+            return
+        time.sleep(0.12)                       # let the sample that covers the end of the region be printed
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        import datetime
+        rows = []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
             try:
-                out = self.proc.communicate(timeout=5)[0]
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[3:7]))
             except Exception:
-                out = ""
-            for line in out.strip().splitlines():
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    self.samples.append(float(f[0])); self.max_mhz = float(f[1])
-                except Exception:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(name)
+                continue
+        self.n_all = len(rows)
+        t0, t1 = (self.t0 or 0.) - 0.1, (self.t1 or time.time()) + 0.1
+        inside = [r for r in rows if t0 <= r[0] <= t1] or rows[-2:]
+        for ts, mhz, mx, flags in inside:
+            self.samples.append(mhz)
+            self.max_mhz = mx
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
+                if "Active" in v and "Not" not in v:
+                    self.reasons.add(name)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["NVML unavailable"]}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples_in_timed_region": len(self.samples), "samples_total": self.n_all, "how": "nvidia-smi -lms 100, started before warm-up"}
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline / reference arm
@@ -343,7 +335,7 @@ def main():
         loss_host.copy_(step(o, d), non_blocking=True)                                # D2H of the step's result
         torch.cuda.current_stream().synchronize()
 
-    with ClockSampler(local) as clocks:          # started before warm-up (NVML's lazy initialisation happens there), records only when armed
+    with ClockSampler(local) as clocks:          # one looping nvidia-smi, forked before the warm-up; samples are attributed by timestamp
         for i in range(args.warmup):
             resident(i)
         torch.cuda.synchronize()
