@@ -374,11 +374,18 @@ def main():
     for key in ("fused_sdf_fwd", "lotd_gather"):
         if key in kt:
             gather = kt[key] if gather is None else {k: gather[k] + kt[key][k] for k in gather}
+    traffic, traffic_note = None, None
+    try:       # dram bytes of the dominant gather launch, from the committed ncu --set full capture (per launch, like `achieved`)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = tj["traffic_bytes_per_launch"]
+        traffic_note = {"unit": "bytes per launch (dram read + write)", "algorithmic_bytes_of_that_launch": tj["algorithmic_bytes_per_launch"], "source": tj["source"]}
+    except Exception:
+        pass
     roof = None
     if gather:
         achieved = gather["units"] * 512.0 / (gather["ms"] * 1e-3) / 1e9     # 512 B of table per encoded point
         roof = {"kernel": "LoTD hash gather: k_fused_sdf_tc (gather + tcgen05 decoder) and k_lotd_fwd", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "points_per_launch": gather["units"] / max(gather["launches"], 1), "launches": gather["launches"],
                 "avg_launch_ms": gather["ms"] / max(gather["launches"], 1), "share_of_step": gather["ms"] / max(sum(t_inst), 1e-9),
                 "per_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kt.items()},
