@@ -258,6 +258,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--rayschunk", type=int, default=H * W, help="rays per render call (default: the whole frame in one call)")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step (default: the full 800x600 frame)")
+    ap.add_argument("--random-rays", action="store_true", help="draw the --rays rays of every pose as random pixels (a training batch) instead of the first rows")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
@@ -288,7 +289,11 @@ def main():
     views_host, views_dev = [], []
     for k in range(N_VIEWS):
         o, d = pinhole_rays(H, W, orbit((k * world + rank) % (N_VIEWS * world), N_VIEWS * world))
-        o, d = o[:n_rays].contiguous(), d[:n_rays].contiguous()
+        if args.random_rays:
+            sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(1000 + k))[:n_rays]
+            o, d = o[sel].contiguous(), d[sel].contiguous()
+        else:
+            o, d = o[:n_rays].contiguous(), d[:n_rays].contiguous()
         views_host.append((o.pin_memory(), d.pin_memory()))
         views_dev.append((o.to(device), d.to(device)))
     h_appear = torch.zeros(args.rayschunk, 4, device=device)
@@ -395,7 +400,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
         "config": {"workload": "cfg2", "model": "LoTDNeuS 16x2 LoTD (12.13M params) + 32-64-1 SDF MLP + 58-64-64-3 radiance MLP",
-                   "frame": "800x600", "rays_per_step_per_gpu": n_rays, "rayschunk": args.rayschunk, "samples_per_ray": "<=116 boundary, <=1024 marched",
+                   "frame": "800x600", "rays_per_step_per_gpu": n_rays, "ray_order": "random pixels" if args.random_rays else "image rows", "rayschunk": args.rayschunk, "samples_per_ray": "<=116 boundary, <=1024 marched",
                    "parallelism": f"dp{world} ray-shard, 1 all-reduce/step", "l2": "256 MiB L2 flush between steps; per-step working set >> 126 MB", "camera_poses": n_views},
         "e2e": {"value": world * n_rays / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(2 * n_rays * 3 * 4), "d2h_bytes_per_step": 4},
@@ -409,7 +414,8 @@ def main():
         # B1 of BASELINE.md, measured in a child process so that none of its module patching can leak into this arm
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--steps", "2", "--warmup", "2",
-                                "--no-cpu-baseline", "--rayschunk", str(args.rayschunk)], capture_output=True, text=True, timeout=600)
+                                "--no-cpu-baseline", "--rayschunk", str(args.rayschunk), "--rays", str(args.rays)] + (["--random-rays"] if args.random_rays else []),
+                               capture_output=True, text=True, timeout=600)
             rl = json.loads(r.stdout.strip().splitlines()[-1])
             line["reference_cuda"] = {"value": rl["value"], "unit": "Mrays/s", "ms_per_step": rl["ms_per_step"], "e2e": rl["e2e"]["value"],
                                       "what": "reference nr3d_lib CUDA kernels compiled from /root/reference (oracle/_ref), same B200, same workload"}
