@@ -103,12 +103,16 @@ int nsb_ray_marching(int64_t n_rays, const float *rays_o, const float *rays_d, c
                      float dt_gamma, uint32_t max_steps, const int32_t *packed_info, int32_t *num_steps,
                      float *t_starts, float *t_ends, int32_t *ridx, int32_t *gidx, int32_t *bidx, void *stream);
 /* The same with the second round restricted to the rays ray_list[0..n_list) (those whose first-round count is non-zero: on an
- * image ~10 % of the rays); ray_list == NULL marches all n_rays.  t_ends / gidx / bidx may be NULL in the second round. */
+ * image ~10 % of the rays); ray_list == NULL marches all n_rays.  t_ends / gidx / bidx may be NULL in the second round.
+ * grid_bits: NULL or nsb_pack_occ_bits(grid_binary). */
 int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
                             const float *roi, const int32_t *batch_inds, int32_t rx, int32_t ry, int32_t rz,
                             const uint8_t *grid_binary, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
                             const int32_t *packed_info, int32_t *num_steps, float *t_starts, float *t_ends, int32_t *ridx,
-                            int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, void *stream);
+                            int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, const uint32_t *grid_bits, void *stream);
+/* words[(cells + 31) / 32]: the bool grid packed 32 cells per word (bit k of word w = cell 32 w + k).  Passing it as `grid_bits`
+ * (single-grid marching only) saves every CTA the re-packing of the 64^3 grid into shared memory. */
+int nsb_pack_occ_bits(const uint8_t *grid_binary, int64_t cells, uint32_t *words, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * _pack_ops  (csrc/pack_ops/pack_ops.cpp:20-58, pack_ops.h:11-65).  fp32 features unless noted.

@@ -26,6 +26,7 @@ struct MarchArgs {
     int32_t *ridx, *gidx, *bidx;
     const int64_t *ray_list;       // second round only: the rays to re-march (those with samples); NULL = all n_rays
     int64_t n_list;
+    const uint32_t *grid_bits;     // optional: the grid already packed 32 cells / word (nsb_pack_occ_bits), copied instead of re-packed per CTA
 };
 
 __device__ __forceinline__ float calc_dt(float t, float dt_gamma, float dt_min, float dt_max) {
@@ -48,6 +49,9 @@ __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
     if (SMEM_BITS) {
         // pack 32 bools per word; each thread builds whole words so no atomics are needed
         const int64_t words = (cells + 31) >> 5;
+        if (a.grid_bits) {
+            for (int64_t w = threadIdx.x; w < words; w += blockDim.x) s_bits[w] = a.grid_bits[w];
+        } else
         for (int64_t w = threadIdx.x; w < words; w += blockDim.x) {
             uint32_t bits = 0;
             const int64_t base = w << 5;
@@ -137,9 +141,30 @@ __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256) k_pack_occ_bits(const uint8_t *__restrict__ grid, int64_t cells, uint32_t *__restrict__ words) {
+    const int64_t n_words = (cells + 31) >> 5;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t bits = 0;
+        const int64_t base = w << 5;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const int64_t c = base + k;
+            if (c < cells && grid[c]) bits |= (1u << k);
+        }
+        words[w] = bits;
+    }
+}
+
 }  // namespace nsb
 
 using namespace nsb;
+
+extern "C" int nsb_pack_occ_bits(const uint8_t *grid_binary, int64_t cells, uint32_t *words, void *stream) {
+    if (cells == 0) return 0;
+    NSB_REQUIRE(grid_binary && words, "nsb_pack_occ_bits: NULL argument");
+    k_pack_occ_bits<<<wave_grid((cells + 31) / 32, 256, 4), 256, 0, (cudaStream_t)stream>>>(grid_binary, cells, words);
+    return check_launch("nsb_pack_occ_bits");
+}
 
 extern "C" int nsb_ray_marching(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min,
                                 const float *t_max, const float *roi, const int32_t *batch_inds, int32_t rx, int32_t ry,
@@ -147,21 +172,22 @@ extern "C" int nsb_ray_marching(int64_t n_rays, const float *rays_o, const float
                                 float dt_gamma, uint32_t max_steps, const int32_t *packed_info, int32_t *num_steps,
                                 float *t_starts, float *t_ends, int32_t *ridx, int32_t *gidx, int32_t *bidx, void *stream) {
     return nsb_ray_marching_listed(n_rays, rays_o, rays_d, t_min, t_max, roi, batch_inds, rx, ry, rz, grid_binary, step_size, max_step_size, dt_gamma,
-                                   max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, nullptr, 0, stream);
+                                   max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
                                        const float *roi, const int32_t *batch_inds, int32_t rx, int32_t ry, int32_t rz,
                                        const uint8_t *grid_binary, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
                                        const int32_t *packed_info, int32_t *num_steps, float *t_starts, float *t_ends, int32_t *ridx,
-                                       int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, void *stream) {
+                                       int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, const uint32_t *grid_bits,
+                                       void *stream) {
     if (n_rays == 0 || (ray_list && n_list == 0)) return 0;
     NSB_REQUIRE(rays_o && rays_d && t_min && t_max && roi && grid_binary, "nsb_ray_marching: NULL input");
     NSB_REQUIRE(rx > 0 && ry > 0 && rz > 0, "nsb_ray_marching: bad grid resolution");
     if (packed_info == nullptr) NSB_REQUIRE(num_steps && !ray_list, "nsb_ray_marching: first round needs num_steps (and marches every ray)");
     else NSB_REQUIRE(t_starts && ridx, "nsb_ray_marching: second round needs t_starts and ridx (t_ends / gidx / bidx are optional)");
     MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, batch_inds, rx, ry, rz, grid_binary, step_size, max_step_size,
-                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, ray_list, n_list};
+                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, ray_list, n_list, grid_bits};
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cells = (int64_t)rx * ry * rz;
     const size_t smem = (size_t)((cells + 31) / 32) * 4;

@@ -199,6 +199,21 @@ def neus_alpha_compact(sdf, inv_s, pack_infos, ridx_all, t_mid, rays_inds, early
 
 
 @torch.no_grad()
+_BITS_CACHE = {}
+
+
+def _occ_bits(occ_grid):
+    """the bool grid packed 32 cells / word, rebuilt only when the grid tensor changed"""
+    key = (occ_grid.data_ptr(), occ_grid._version, tuple(occ_grid.shape))
+    hit = _BITS_CACHE.get("k")
+    if hit is None or hit[0] != key:
+        cells = occ_grid.numel()
+        words = torch.empty((cells + 31) // 32, dtype=torch.int32, device=occ_grid.device)
+        L.check(L.lib().nsb_pack_occ_bits(L.ptr(occ_grid.contiguous().view(torch.uint8), "u8"), L.c_i64(cells), L.ptr(words), L.stream_ptr()), "pack_occ_bits")
+        hit = _BITS_CACHE["k"] = (key, words, occ_grid)       # holds the grid: a freed + reallocated tensor cannot alias the key
+    return hit[1]
+
+
 def march_lean(occ_grid, rays_o, rays_d, near, far, *, step_size, max_steps, max_step_size=1e10, dt_gamma=0.0, roi=None):
     """occgrid_raymarch (graphics/raymarch.py) reduced to what the NeuS query consumes, without the per-sample temporaries:
     -> None if no ray hits an occupied voxel, else (ridx_hit [n_hit] i64, pack_infos [n_hit,2] i64, t_starts [M] f32, ridx [M] i64)."""
@@ -211,8 +226,10 @@ def march_lean(occ_grid, rays_o, rays_d, near, far, *, step_size, max_steps, max
             L.ptr(roi, "f32", "roi"), None, L.c_i32(res[0]), L.c_i32(res[1]), L.c_i32(res[2]), L.ptr(g, "u8"), L.c_f32(step_size),
             L.c_f32(max_step_size), L.c_f32(dt_gamma), ctypes.c_uint32(int(max_steps)))
     num_steps = torch.empty(R, dtype=torch.int32, device=dev)
+    bits = _occ_bits(occ_grid) if occ_grid.numel() * 4 // 32 <= 96 * 1024 else None
     with L.KERNEL_TIMER.time("march", R):
-        L.check(L.lib().nsb_ray_marching(*args, None, L.ptr(num_steps), None, None, None, None, None, L.stream_ptr()), "ray_marching")
+        L.check(L.lib().nsb_ray_marching_listed(*args, None, L.ptr(num_steps), None, None, None, None, None, None, L.c_i64(0),
+                                                L.ptr(bits, allow_none=True), L.stream_ptr()), "ray_marching")
     sc = scan_counts(num_steps, want_info2=True, want_index=True, want_pack=True)
     M = sc["total"]
     if M == 0:
@@ -221,7 +238,8 @@ def march_lean(occ_grid, rays_o, rays_d, near, far, *, step_size, max_steps, max
     ridx = torch.empty(M, dtype=torch.int32, device=dev)
     with L.KERNEL_TIMER.time("march", R):
         L.check(L.lib().nsb_ray_marching_listed(*args, L.ptr(sc["info2"]), None, L.ptr(t_starts), None, L.ptr(ridx), None, None,
-                                                L.ptr(sc["index"], "i64"), L.c_i64(sc["n_nonzero"]), L.stream_ptr()), "ray_marching")
+                                                L.ptr(sc["index"], "i64"), L.c_i64(sc["n_nonzero"]), L.ptr(bits, allow_none=True), L.stream_ptr()),
+                    "ray_marching")
     return sc["index"], sc["pack"], t_starts, ridx.long()
 
 
