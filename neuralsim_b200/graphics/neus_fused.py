@@ -198,10 +198,10 @@ def neus_alpha_compact(sdf, inv_s, pack_infos, ridx_all, t_mid, rays_inds, early
     return dict(alpha=alpha_k, ridx=ridx_c, t=t_c, pack_infos=sc["pack"], nidx=sc["index"], rays_inds_hit=sc["src"], pidx=pidx)
 
 
-@torch.no_grad()
 _BITS_CACHE = {}
 
 
+@torch.no_grad()
 def _occ_bits(occ_grid):
     """the bool grid packed 32 cells / word, rebuilt only when the grid tensor changed"""
     key = (occ_grid.data_ptr(), occ_grid._version, tuple(occ_grid.shape))
@@ -214,6 +214,7 @@ def _occ_bits(occ_grid):
     return hit[1]
 
 
+@torch.no_grad()
 def march_lean(occ_grid, rays_o, rays_d, near, far, *, step_size, max_steps, max_step_size=1e10, dt_gamma=0.0, roi=None):
     """occgrid_raymarch (graphics/raymarch.py) reduced to what the NeuS query consumes, without the per-sample temporaries:
     -> None if no ray hits an occupied voxel, else (ridx_hit [n_hit] i64, pack_infos [n_hit,2] i64, t_starts [M] f32, ridx [M] i64)."""

@@ -64,3 +64,16 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "from .. import oracle" in src:
                     bad.append(f)
     assert not bad, bad
+
+
+def test_every_python_module_imports():
+    """A syntax / import error anywhere in the package must fail the CPU suite, not the first GPU call."""
+    import importlib
+    import pkgutil
+
+    import neuralsim_b200
+    for m in pkgutil.walk_packages(neuralsim_b200.__path__, "neuralsim_b200."):
+        if not m.name.rsplit(".", 1)[-1].startswith("lib"):          # libneuralsim_b200.so is the C ABI, not a Python extension
+            importlib.import_module(m.name)
+    import bench  # noqa: F401
+    import __graft_entry__  # noqa: F401
