@@ -67,27 +67,37 @@ def launch_count() -> int:
 
 
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """raw cudaStream_t of torch's current stream on the current device (the C-level getter: torch.cuda.current_stream() builds a
+    Python Stream object and costs ~17 us per call -- 0.5 ms per step at 30 launches)"""
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    except AttributeError:       # private API moved: fall back to the public one
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 _DT = {"f32": torch.float32, "f16": torch.float16, "i64": torch.int64, "i32": torch.int32, "u8": torch.uint8,
        "bool": torch.bool}
 
 
+_NULL = ctypes.c_void_p(0)
+
+
 def ptr(t, dtype=None, name="tensor", allow_none=False):
     """Device pointer of a contiguous CUDA tensor (raises otherwise)."""
     if t is None:
         if allow_none:
-            return ctypes.c_void_p(0)
+            return _NULL
         raise RuntimeError(f"{name} must not be None")
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
-        raise RuntimeError(f"{name} must be a CUDA tensor (neuralsim_b200 has no CPU path)")
-    if not t.is_contiguous():
+    try:
+        ok = t.is_cuda and t.is_contiguous()
+    except AttributeError:
+        ok = False
+    if not ok:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor (neuralsim_b200 has no CPU path)")
         raise RuntimeError(f"{name} must be contiguous")
-    if dtype is not None:
-        want = _DT[dtype] if isinstance(dtype, str) else dtype
-        if t.dtype != want:
-            raise RuntimeError(f"{name} must have dtype {want}, got {t.dtype}")
+    if dtype is not None and t.dtype is not (_DT[dtype] if dtype.__class__ is str else dtype):
+        raise RuntimeError(f"{name} must have dtype {_DT[dtype] if isinstance(dtype, str) else dtype}, got {t.dtype}")
     return ctypes.c_void_p(t.data_ptr())
 
 

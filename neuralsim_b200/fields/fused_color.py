@@ -50,7 +50,13 @@ class _FusedColor(autograd.Function):
             raise RuntimeError("fused_color: backward through a forward that ran without grad")
         dev, n = rgb.device, ctx.n
         meta = ctx.model.implicit_surface.encoding.meta
-        grads = [torch.zeros(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
+        # one zero-fill for the table gradient, one for the ten small tensors (views of a flat buffer)
+        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes[1:]]
+        small = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        grads, o = [torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dev)], 0
+        for sh, k in zip(ctx.shapes[1:], sizes):
+            grads.append(small[o:o + k].view(sh))
+            o += k
         if g_sdf is None and g_nab is None and g_rgb is None:
             return (None,) * 6 + tuple(grads)
         ridx, t, rays_o, rays_d = ctx.pts

@@ -173,8 +173,10 @@ class _FusedSDF(autograd.Function):
         meta, dev = ctx.owner.encoding.meta, d_sdf.device
         gs, w1s, b1s, w2s, b2s = ctx.shapes
         d_grid = torch.zeros(gs, dtype=torch.float32, device=dev)
-        d_W1, d_b1 = torch.zeros(w1s, dtype=torch.float32, device=dev), torch.zeros(b1s, dtype=torch.float32, device=dev)
-        d_W2, d_b2 = torch.zeros(w2s, dtype=torch.float32, device=dev), torch.zeros(b2s, dtype=torch.float32, device=dev)
+        ks = [int(torch.Size(x).numel()) for x in (w1s, b1s, w2s, b2s)]
+        small = torch.zeros(sum(ks), dtype=torch.float32, device=dev)         # one zero-fill for the four decoder gradients
+        d_W1, d_b1 = small[:ks[0]].view(w1s), small[ks[0]:ks[0] + ks[1]].view(b1s)
+        d_W2, d_b2 = small[ks[0] + ks[1]:ks[0] + ks[1] + ks[2]].view(w2s), small[ks[0] + ks[1] + ks[2]:].view(b2s)
         d_sdf = d_sdf.contiguous().float()
         # Most boundary points of a NeuS ray carry an exactly-zero cotangent (saturated sigmoid far from the surface, samples
         # behind the early-stop): only the others are recomputed (the reference's scatter kernel skips them one by one).

@@ -246,11 +246,13 @@ def volume_integration(volume_buffer, rendered, training=True, depth_use_normali
         if nab is not None and not training:
             nab = F.normalize(nab.clamp(-1, 1), dim=-1)
         rgb = volume_buffer.get("rgb") if "rgb_volume" in rendered else None
-        if fresh and rendered["mask_volume"].dim() == 1:
+        n_img = getattr(rendered, "_n", None)               # renderer._LazyZeros: nothing allocated yet
+        if fresh and n_img is None and rendered["mask_volume"].dim() == 1:
+            n_img = rendered["mask_volume"].shape[0]
+        if fresh and n_img is not None:
             # `rendered` holds nothing yet (all zeros): the kernel writes whole-image buffers at rays_inds_hit directly
             vw, m, d, c, nn_ = neus_fused.composite(volume_buffer["opacity_alpha"], volume_buffer["t"], volume_buffer["pack_infos_hit"], rgb=rgb,
-                                                     nablas=nab, normalize_depth=depth_use_normalized_vw, ray_index=hit,
-                                                     n_rays=rendered["mask_volume"].shape[0])
+                                                     nablas=nab, normalize_depth=depth_use_normalized_vw, ray_index=hit, n_rays=n_img)
             volume_buffer["vw"] = vw
             rendered["mask_volume"], rendered["depth_volume"] = m, d
             if c is not None:

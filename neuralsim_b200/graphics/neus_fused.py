@@ -252,15 +252,14 @@ class _Composite(torch.autograd.Function):
         nb = None if nablas is None else _f32c(nablas)
         P, dev = pack_infos.shape[0], a.device
         vw = torch.empty_like(a)
-        if ray_index is None:
-            new = lambda *shape: torch.empty(*shape, device=dev)
-            n_out = P
-        else:                                       # outputs are whole-image buffers; rays without a pack stay 0
-            new = lambda *shape: torch.zeros(*shape, device=dev)
-            n_out = int(n_rays)
-        mask, depth = new(n_out), new(n_out)
-        rgb_o = new(n_out, 3) if r is not None else None
-        nab_o = new(n_out, 3) if nb is not None else None
+        n_out = P if ray_index is None else int(n_rays)
+        cols = 2 + (3 if r is not None else 0) + (3 if nb is not None else 0)
+        # whole-image buffers (rays without a pack stay 0): one allocation / zero-fill, four contiguous views
+        buf = (torch.empty if ray_index is None else torch.zeros)(cols * n_out, device=dev)
+        mask, depth = buf[:n_out], buf[n_out:2 * n_out]
+        rgb_o = buf[2 * n_out:5 * n_out].view(n_out, 3) if r is not None else None
+        o3 = 5 * n_out if r is not None else 2 * n_out
+        nab_o = buf[o3:o3 + 3 * n_out].view(n_out, 3) if nb is not None else None
         L.check(L.lib().nsb_composite_forward(L.ptr(a, "f32"), L.ptr(tt, "f32"), L.ptr(r, "f32", allow_none=True),
                                               L.ptr(nb, "f32", allow_none=True), L.ptr(pack_infos, "i64"), L.c_i64(P), L.c_f32(early_stop_eps),
                                               L.c_f32(alpha_thre), ctypes.c_int(1 if normalize_depth else 0), L.ptr(ray_index, "i64", allow_none=True),

@@ -14,6 +14,34 @@ import torch
 from .fields.neus import LoTDNeuSModel, volume_integration
 
 
+class _LazyZeros(dict):
+    """The `rendered` dict of one chunk: zero images that are only allocated if somebody reads them (the fused integration replaces
+    them wholesale, so a chunk that hits the object never pays for the four zero-fills)."""
+
+    def __init__(self, n, device, with_rgb, with_normal):
+        super().__init__()
+        self._n, self._device = n, device
+        self._shapes = dict(depth_volume=(n,), mask_volume=(n,))
+        if with_rgb:
+            self._shapes["rgb_volume"] = (n, 3)
+        if with_normal:
+            self._shapes["normals_volume"] = (n, 3)
+
+    def __missing__(self, k):
+        if k not in self._shapes:
+            raise KeyError(k)
+        v = self[k] = torch.zeros(*self._shapes[k], device=self._device)
+        return v
+
+    def __contains__(self, k):
+        return k in self._shapes or dict.__contains__(self, k)
+
+    def materialise(self):
+        for k in self._shapes:
+            self[k]
+        return dict(self)
+
+
 class SingleVolumeRenderer:
     def __init__(self, config: dict = None):
         cfg = dict(near=0.01, far=None, with_rgb=True, with_normal=True, perturb=False, rayschunk=0, depth_use_normalized_vw=True)
@@ -41,11 +69,7 @@ class SingleVolumeRenderer:
         n, device = rays_o.shape[0], rays_o.device
         extra = {} if rays_h_appear is None else dict(rays_h_appear=rays_h_appear)
         ray_tested = model.ray_test(rays_o, rays_d, near=near, far=far, **extra)
-        rendered = dict(depth_volume=torch.zeros(n, device=device), mask_volume=torch.zeros(n, device=device))
-        if cfg["with_rgb"]:
-            rendered["rgb_volume"] = torch.zeros(n, 3, device=device)
-        if cfg["with_normal"]:
-            rendered["normals_volume"] = torch.zeros(n, 3, device=device)
+        rendered = _LazyZeros(n, device, cfg["with_rgb"], cfg["with_normal"])     # buffers nobody overwrites are materialised on first use
         ret = dict(rendered=rendered, ray_tested=ray_tested)
         qcfg = dict(model.ray_query_cfg)
         qcfg.update(with_rgb=cfg["with_rgb"], with_normal=cfg["with_normal"], perturb=cfg["perturb"])
@@ -56,6 +80,7 @@ class SingleVolumeRenderer:
                 # obj -> world rotation is the identity for a single static object (single_volume_renderer.py:262-276)
                 vb["nablas_in_world"] = vb["nablas"]
             self._volume_integration(vb, rendered, fresh=True)
+        ret["rendered"] = rendered.materialise()
         if return_buffer:
             ret["volume_buffer"] = vb
         if return_details:

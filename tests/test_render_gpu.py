@@ -93,3 +93,50 @@ def test_no_hit_and_empty_inputs(cuda):
     assert torch.isfinite(out["rgb_volume"]).all()
     out = r.render(model, ro[:0].to(cuda), rd[:0].to(cuda), rays_h_appear=torch.zeros(0, 4, device=cuda))["rendered"]
     assert out["rgb_volume"].shape == (0, 3)
+
+
+def test_full_frame_size_independent_properties(cuda):
+    """BASELINE.json's full size (one 800x600 frame, 480 000 rays, ~30 M SDF queries; far beyond what the CPU oracle finishes): properties that
+    need no oracle -- (1) rays are independent: the frame rendered in one call (image-ordered rays -> ray-tiled kernels), in chunks, and as a
+    random permutation of its rays (incoherent rays -> ray-major kernels) is the same image; (2) so are the parameter gradients;
+    (3) the mask is a transmittance complement in [0, 1]; depth lies inside the ray's box interval; pixels that miss the sphere render 0."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from neuralsim_b200.renderer import SingleVolumeRenderer
+    model = bench.build_model(cuda).train()
+    ro, rd = bench.pinhole_rays(bench.H, bench.W, bench.orbit(1, 8))
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    ha = torch.zeros(ro.shape[0], 4, device=cuda)
+    ren = SingleVolumeRenderer(dict(near=0.01)).train()
+
+    def run(o, d, chunk):
+        model.zero_grad(set_to_none=True)
+        outs, n = [], o.shape[0]
+        for s in range(0, n, chunk):
+            out = ren.render(model, o[s:s + chunk], d[s:s + chunk], rays_h_appear=ha[:min(chunk, n - s)])["rendered"]
+            loss = sum(v.sum() for v in out.values()) / n
+            if loss.requires_grad:
+                loss.backward()
+            outs.append({k: v.detach() for k, v in out.items()})
+        g = model.implicit_surface.encoding.flattened_params.grad.clone()
+        gw = model.radiance_net.blocks.layers[0].weight.grad.clone()
+        return {k: torch.cat([o_[k] for o_ in outs], 0) for k in outs[0]}, g, gw
+
+    full, g_full, gw_full = run(ro, rd, ro.shape[0])
+    chunked, g_ch, gw_ch = run(ro, rd, 100_000)
+    perm = torch.randperm(ro.shape[0], device=cuda, generator=torch.Generator(device=cuda).manual_seed(0))
+    shuf, g_sh, gw_sh = run(ro[perm].contiguous(), rd[perm].contiguous(), ro.shape[0])
+    for k in full:
+        assert rel_l2(chunked[k], full[k]) <= 1e-6, k
+        assert rel_l2(shuf[k], full[k][perm]) <= 1e-6, k
+    for a, b in ((g_ch, g_full), (g_sh, g_full), (gw_ch, gw_full), (gw_sh, gw_full)):
+        assert rel_l2(a, b) <= 2e-3                       # fp32 atomics: summation order
+    m = full["mask_volume"]
+    assert float(m.min()) >= 0.0 and float(m.max()) <= 1.0 + 1e-5
+    hit = m > 0.5
+    assert 0.05 < float(hit.float().mean()) < 0.2          # the sphere of radius 0.5 seen from 3 units covers ~9 % of the frame
+    dep = full["depth_volume"][hit]
+    assert float(dep.min()) > 2.0 and float(dep.max()) < 3.2
+    assert float(full["rgb_volume"][~(m > 0)].abs().max()) == 0.0
