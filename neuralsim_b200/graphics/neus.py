@@ -91,10 +91,11 @@ def neus_ray_sdf_to_upsample_alpha(sdf, depth_samples, inv_s):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, with_rgb, with_normal, nablas_has_grad, forward_inv_s, num_coarse, march_cfg, num_fine,
+def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, perturb=False, with_rgb, with_normal, nablas_has_grad, forward_inv_s, num_coarse, march_cfg, num_fine,
                  upsample_inv_s, factors, use_estimate_alpha):
     """The query below with every stage between the big kernels as ONE launch (csrc/neus_glue.cu, csrc/neus_fused.cu) and three host
-    reads in total (march size, compression size, + the ray test's): same samples, same values as the chain it replaces -- the chain
+    reads in total (march size, compression size, + the ray test's): same samples, same values as the chain it replaces (with `perturb`,
+    the same random stream too) -- the chain
     stays in this file as the specification (tests/test_neus_fused_gpu.py runs both).  None -> no ray marched into an occupied voxel
     (the caller falls back to the general path for that rare case)."""
     rays_o, rays_d, near, far, rays_inds = itemgetter("rays_o", "rays_d", "near", "far", "rays_inds")(ray_tested)
@@ -105,11 +106,15 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, with_rgb, with_
     mc["dt_gamma"] = mc.get("dt_gamma", 0.0) * fac
     mc.setdefault("max_steps", 512)
     rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
-    depths_coarse_1 = batch_sample_step_linear(near, far, num_coarse + 1, prefix_shape=[rays_o.shape[0]])
+    depths_coarse_1 = batch_sample_step_linear(near, far, num_coarse + 1, prefix_shape=[rays_o.shape[0]], perturb=perturb)
     marched = neus_fused.march_lean(model.accel.occ.occ_grid, rays_o, rays_d, near.contiguous(), far.contiguous(), **mc)
     if marched is None:
         return None
     ridx_hit, pinfo_march, depth_samples, ridx = marched
+    if perturb:
+        # the single-grid marcher jitters only `deltas` (occgrid_raymarch.py:96-110), which this query never reads; the draw is made
+        # anyway so that the random stream -- and therefore every later sample -- is the one the op-by-op chain consumes
+        torch.rand(depth_samples.shape, dtype=depth_samples.dtype, device=depth_samples.device)
     pack_infos = pinfo_march
     coherent = bool(ray_tested.get("rays_coherent", False))      # image-ordered rays: ray-tiled traversal inside the SDF kernel
     with torch.no_grad():
@@ -117,7 +122,10 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, with_rgb, with_
         fine_stages = []
         for i, factor in enumerate(factors):
             cdf = neus_fused.upsample_cdf(sdf, depth_samples, pack_infos, upsample_inv_s * factor, use_estimate_alpha)
-            fine = neus_fused.sample_cdf_uniform(depth_samples, cdf, pack_infos, num_fine[i])
+            if perturb:                  # one stratified u per pack and sample (raysample.py:38-61)
+                fine = packed_sample_cdf(depth_samples, cdf, pack_infos, num_fine[i], perturb=True)[0]
+            else:
+                fine = neus_fused.sample_cdf_uniform(depth_samples, cdf, pack_infos, num_fine[i])
             fine_stages.append(fine)
             if i < n_stage - 1:         # (the reference also merges after the last stage; nothing reads that result)
                 packs = (get_pack_infos_from_batch(ridx_hit.shape[0], fine.shape[1], device=fine.device), ridx_hit) if coherent else None
@@ -190,11 +198,11 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
     dir_scale = rays_d.detach().norm(dim=-1)
     view_dirs = rays_d / dir_scale.clamp_min(1.0e-10).unsqueeze(-1) if use_view_dirs else None
 
-    if (FUSED_STAGES and not perturb and num_coarse > 0 and rays_o.is_cuda and dtype == torch.float32 and hasattr(model, "forward_sdf_on_rays")
+    if (FUSED_STAGES and num_coarse > 0 and rays_o.is_cuda and dtype == torch.float32 and hasattr(model, "forward_sdf_on_rays")
             and getattr(getattr(model.accel, "occ", None), "occ_grid", None) is not None and model.accel.occ.occ_grid.dim() == 3
             and not (rays_o.requires_grad or rays_d.requires_grad or near.requires_grad or far.requires_grad)
             and set(march_cfg) <= {"step_size", "max_steps", "max_step_size", "dt_gamma", "step_size_factor"}):
-        ret = _query_fused(model, ray_tested, view_dirs, rays_h_appear, with_rgb=with_rgb, with_normal=with_normal, nablas_has_grad=nablas_has_grad,
+        ret = _query_fused(model, ray_tested, view_dirs, rays_h_appear, perturb=perturb, with_rgb=with_rgb, with_normal=with_normal, nablas_has_grad=nablas_has_grad,
                            forward_inv_s=forward_inv_s, num_coarse=num_coarse, march_cfg=march_cfg, num_fine=num_fine, upsample_inv_s=upsample_inv_s,
                            factors=upsample_inv_s_factors, use_estimate_alpha=upsample_use_estimate_alpha)
         if ret is not None:

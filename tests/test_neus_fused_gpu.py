@@ -111,8 +111,10 @@ def test_composite_forward_backward(normalize_depth):
         assert rel_l2(x, y) < 1e-5
 
 
-def test_render_fused_equals_unfused_chain():
-    """The whole query + integration with the fused stages on and off: same samples, same image, same gradients."""
+@pytest.mark.parametrize("perturb", [False, True])
+def test_render_fused_equals_unfused_chain(perturb):
+    """The whole query + integration with the fused stages on and off: same samples, same image, same gradients
+    (with `perturb`, from the same seed: the fused path consumes the random stream exactly as the op-by-op chain does)."""
     from neuralsim_b200.graphics import neus as G
     from neuralsim_b200.renderer import SingleVolumeRenderer
     from oracle import scene as oscene
@@ -120,13 +122,14 @@ def test_render_fused_equals_unfused_chain():
     P, model = make_pair("cuda")
     rays_o, rays_d = oscene.pinhole_rays(36, 48, oscene.orbit_camera(1, 8, radius=3.0, elev_deg=25.0))
     rays_o, rays_d = rays_o.cuda(), rays_d.cuda()
-    ren = SingleVolumeRenderer(dict(near=0.01, far=None))
+    ren = SingleVolumeRenderer(dict(near=0.01, far=None, perturb=perturb))
     h_appear = torch.linspace(-0.5, 0.5, rays_o.shape[0] * 4, device="cuda").view(-1, 4).contiguous()
     outs = {}
     for fused in (True, False):
         G.FUSED_STAGES = fused
         try:
             model.zero_grad(set_to_none=True)
+            torch.manual_seed(123)
             ret = ren.render(model, rays_o, rays_d, rays_h_appear=h_appear, return_buffer=True)
             r = ret["rendered"]
             (r["rgb_volume"].square().sum() + r["depth_volume"].sum() * 0.1 + r["mask_volume"].sum() * 0.3
