@@ -144,7 +144,8 @@ class ClockSampler:
         phys = vis.split(",")[self.index].strip() if vis and len(vis.split(",")) > self.index else str(self.index)
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", phys],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.first = self.proc.stdout.readline()     # block until its (slow, driver-heavy) start-up is over: it must not overlap the timed loops
         except Exception:
             self.proc = None
         return self
@@ -155,7 +156,7 @@ class ClockSampler:
         time.sleep(0.12)                       # let the sample that covers the end of the region be printed
         self.proc.terminate()
         try:
-            out = self.proc.communicate(timeout=5)[0]
+            out = getattr(self, "first", "") + self.proc.communicate(timeout=5)[0]
         except Exception:
             out = ""
         import datetime
@@ -405,6 +406,7 @@ def main():
         "e2e": {"value": world * n_rays / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(2 * n_rays * 3 * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof,
+        "step_ms": {"resident": [round(x, 3) for x in t_res], "e2e": [round(x, 3) for x in t_e2e]},
     }
     if args.impl == "reference-cuda":
         line["impl"] = "reference-cuda"
