@@ -57,7 +57,7 @@ def orbit(k, n, radius=3.0, elev_deg=20.0):
     return (radius * math.cos(e) * math.cos(a), radius * math.cos(e) * math.sin(a), radius * math.sin(e))
 
 
-def build_model(device, seed=42, radius=0.5, noise=2.0e-3, ln_inv_s_init=0.5298, k_pass=8.0):
+def build_model(device, seed=42, radius=0.5, noise=2.0e-3, ln_inv_s_init=0.5298, k_pass=8.0, collect_samples=False):
     """CFG-sized model whose SDF is a noisy sphere (the state `pretrain_sdf_sphere` would reach; see oracle/scene.py for
     the same construction on the oracle side).  inv_s = exp(10 * 0.5298) ~ 200."""
     from neuralsim_b200.fields import LoTDNeuSModel
@@ -69,7 +69,7 @@ def build_model(device, seed=42, radius=0.5, noise=2.0e-3, ln_inv_s_init=0.5298,
         radiance_cfg=dict(n_appear_embedding=4, dir_embed_cfg=dict(type="spherical", degree=4), D=2, W=64),
         var_ctrl_cfg=dict(ln_inv_s_init=ln_inv_s_init, ln_inv_s_factor=10.0),
         accel_cfg=dict(resolution=[64, 64, 64], occ_val_fn_cfg=dict(type="sdf", inv_s=256.0), occ_thre=0.3, ema_decay=0.95,
-                       update_from_samples_cfg=None),
+                       update_from_samples_cfg=dict() if collect_samples else None),
         ray_query_cfg=dict(query_mode="march_occ_multi_upsample_compressed", query_param=dict(
             nablas_has_grad=True, num_coarse=64, num_fine=[8, 8, 32], coarse_step_cfg=dict(step_mode="linear"),
             march_cfg=dict(step_size=0.005, max_steps=4096), upsample_inv_s=64.0, upsample_inv_s_factors=[1, 4, 16],
@@ -260,6 +260,8 @@ def main():
     ap.add_argument("--rayschunk", type=int, default=H * W, help="rays per render call (default: the whole frame in one call)")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step (default: the full 800x600 frame)")
     ap.add_argument("--random-rays", action="store_true", help="draw the --rays rays of every pose as random pixels (a training batch) instead of the first rows")
+    ap.add_argument("--collect-samples", action="store_true", help="accel.update_from_samples_cfg = {} as in the shipped training config: every "
+                    "training-time SDF query also feeds the occupancy grid's evidence buffer (in-kernel here, torch_scatter in the reference)")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
@@ -283,7 +285,7 @@ def main():
     from neuralsim_b200.renderer import SingleVolumeRenderer
     if args.impl == "reference-cuda" and not use_reference_cuda_kernels():
         raise SystemExit("bench.py: oracle/_ref is not built (python oracle/build_ref.py in the build container)")
-    model = build_model(device).train()
+    model = build_model(device, collect_samples=args.collect_samples).train()
     renderer = SingleVolumeRenderer(dict(near=0.01, rayschunk=0)).train()
     flat, params = flat_grad_views(model)
     n_rays = args.rays
@@ -348,6 +350,9 @@ def main():
         if world > 1:
             dist.barrier()
         launches0 = _lib.launch_count()
+        import gc
+        gc.collect()
+        gc.disable()                           # no collector pause inside a 15 ms step; re-enabled right after the timed loops
         clocks.armed = True
         t_res = timed(resident, args.steps)
         launches = _lib.launch_count() - launches0
@@ -355,6 +360,7 @@ def main():
             dist.barrier()
         t_e2e = timed(e2e, args.steps)
         clocks.armed = False
+        gc.enable()
         # a separate, instrumented pass for the roofline: CUDA events around every launch of our kernels (not part of `value`)
         _lib.KERNEL_TIMER.enable()
         t_inst = timed(resident, args.steps)
@@ -401,7 +407,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
         "config": {"workload": "cfg2", "model": "LoTDNeuS 16x2 LoTD (12.13M params) + 32-64-1 SDF MLP + 58-64-64-3 radiance MLP",
-                   "frame": "800x600", "rays_per_step_per_gpu": n_rays, "ray_order": "random pixels" if args.random_rays else "image rows", "rayschunk": args.rayschunk, "samples_per_ray": "<=116 boundary, <=1024 marched",
+                   "frame": "800x600", "rays_per_step_per_gpu": n_rays, "ray_order": "random pixels" if args.random_rays else "image rows", "collect_samples": bool(args.collect_samples), "rayschunk": args.rayschunk, "samples_per_ray": "<=116 boundary, <=1024 marched",
                    "parallelism": f"dp{world} ray-shard, 1 all-reduce/step", "l2": "256 MiB L2 flush between steps; per-step working set >> 126 MB", "camera_poses": n_views},
         "e2e": {"value": world * n_rays / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(2 * n_rays * 3 * 4), "d2h_bytes_per_step": 4},
@@ -416,7 +422,8 @@ def main():
         # B1 of BASELINE.md, measured in a child process so that none of its module patching can leak into this arm
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--steps", "2", "--warmup", "2",
-                                "--no-cpu-baseline", "--rayschunk", str(args.rayschunk), "--rays", str(args.rays)] + (["--random-rays"] if args.random_rays else []),
+                                "--no-cpu-baseline", "--rayschunk", str(args.rayschunk), "--rays", str(args.rays)] + (["--random-rays"] if args.random_rays else [])
+                               + (["--collect-samples"] if args.collect_samples else []),
                                capture_output=True, text=True, timeout=600)
             rl = json.loads(r.stdout.strip().splitlines()[-1])
             line["reference_cuda"] = {"value": rl["value"], "unit": "Mrays/s", "ms_per_step": rl["ms_per_step"], "e2e": rl["e2e"]["value"],

@@ -177,9 +177,24 @@ typedef struct nsb_sdf_decoder {       /* LoTDSDF decoder 32->W->1, Softplus(bet
     float beta;                        /* 100 */
 } nsb_sdf_decoder;
 
+/* Optional side effect of every training-time SDF query: `accel.collect_samples(x, sdf)` (renderer_mixin.py:154-164 ->
+ * OccGridEma._collect_samples, ema_single.py:201-203 -> update_occ_val_grid_(grid_pcl, pts, occ_val_fn(sdf), ema_decay = 1), utils.py:93-109):
+ * grid_pcl[voxel(x)] = max(grid_pcl[voxel(x)], (1 / cosh(clamp(inv_s sdf / 2, -20, 20)))^2), evaluated in fp16 like the reference
+ * (its sdf is a half tensor), accumulated with an atomic max inside the query kernel.  Pass NULL to disable. */
+typedef struct nsb_occ_collect {
+    float *grid_pcl;                   /* fp32 [res0, res1, res2], values >= 0 */
+    int32_t res[3];
+    float inv_s;
+} nsb_occ_collect;
+
 /* forward_sdf on N points: x in network space [-1,1]^3 (not yet /2+0.5).  sdf fp32 (fp16-valued). */
 int nsb_fused_sdf(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host,
                   const float *x, int64_t n, int32_t max_level, float *sdf, void *h_out_half, void *stream);
+/* the three queries below with the occupancy-evidence side effect (collect may be NULL = the plain query) */
+int nsb_fused_sdf_collect(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host, const float *x,
+                          const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
+                          const int64_t *pack_infos, const int64_t *pack_ray, int64_t n_packs, int32_t mode, int32_t max_level, float *sdf,
+                          const nsb_occ_collect *collect, void *stream);
 
 /* x = o[ridx] + d[ridx] * t, then forward_sdf.  ridx int64[N] indexes rays_o / rays_d [R,3]. */
 int nsb_fused_sdf_rays(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host,
@@ -291,11 +306,12 @@ typedef struct nsb_color_net {
 int64_t nsb_color_tile_bytes(int64_t n);
 /* Points are x[n,3] or rays_o/rays_d[R,3] + ridx[n] (NULL = identity) + t[n]; view_dirs[R,3] and h_appear[R,n_appear] are
  * indexed by ridx (by the point index when ridx is NULL).  Outputs fp32: sdf[n], nablas[n,3], rgb[n,3], x_out[n,3] (optional).
- * act_* : four buffers of nsb_color_tile_bytes(n) each kept for the backward, or all NULL for inference. */
+ * act_* : four buffers of nsb_color_tile_bytes(n) each kept for the backward, or all NULL for inference.
+ * collect: NULL or the occupancy-evidence side effect of forward_sdf_nablas (see nsb_occ_collect). */
 int nsb_fused_color_fwd(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_color_net *net_host, const float *x,
                         const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, const float *view_dirs,
                         const float *h_appear, int64_t n, int32_t max_level, float *sdf, float *nablas, float *rgb, float *x_out,
-                        void *act_z, void *act_x, void *act_y1, void *act_y2, void *stream);
+                        void *act_z, void *act_x, void *act_y1, void *act_y2, const nsb_occ_collect *collect, void *stream);
 /* Cotangents g_sdf[n], g_nablas[n,3], g_rgb[n,3] (each may be NULL = zero); dh_scratch[n,32] fp32 workspace.
  * All gradient outputs are fp32 and ACCUMULATED into (caller zero-fills); d_R* use the reference's column order. */
 int nsb_fused_color_bwd(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_color_net *net_host, const float *x,

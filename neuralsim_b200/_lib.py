@@ -39,6 +39,10 @@ class ColorNetC(ctypes.Structure):
         ("beta", ctypes.c_float), ("nablas_scale", ctypes.c_float * 3)]
 
 
+class OccCollectC(ctypes.Structure):
+    _fields_ = [("grid_pcl", ctypes.c_void_p), ("res", ctypes.c_int32 * 3), ("inv_s", ctypes.c_float)]
+
+
 _lib = None
 
 

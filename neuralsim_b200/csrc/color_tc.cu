@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kTile)
 k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev net, const PointSrc ps, const float *__restrict__ view_dirs,
             const float *__restrict__ h_appear, int64_t n, int max_level, float *__restrict__ sdf_out, float *__restrict__ nab_out,
             float *__restrict__ rgb_out, float *__restrict__ x_out, uint8_t *__restrict__ Zt, uint8_t *__restrict__ Xt,
-            uint8_t *__restrict__ Y1t, uint8_t *__restrict__ Y2t) {
+            uint8_t *__restrict__ Y1t, uint8_t *__restrict__ Y2t, const OccCollect oc) {
     extern __shared__ uint8_t dyn_smem[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
     uint8_t *sX = tiles;                                       // 16 KB [h | x sh n ha 0]
@@ -344,6 +344,7 @@ k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev n
         }
         if (valid) {
             sdf_out[i] = sdf;
+            if (oc.pcl) occ_collect_point(oc, xs, sdf);
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 nab_out[i * 3 + d] = nab[d];
@@ -807,7 +808,7 @@ extern "C" int64_t nsb_color_tile_bytes(int64_t n) { return ((n + kTile - 1) / k
 extern "C" int nsb_fused_color_fwd(const nsb_lotd_meta *meta, const void *params_half, const nsb_color_net *net, const float *x, const float *rays_o,
                                    const float *rays_d, const int64_t *ridx, const float *t, const float *view_dirs, const float *h_appear,
                                    int64_t n, int32_t max_level, float *sdf, float *nablas, float *rgb, float *x_out, void *act_z, void *act_x,
-                                   void *act_y1, void *act_y2, void *stream) {
+                                   void *act_y1, void *act_y2, const nsb_occ_collect *collect, void *stream) {
     if (n == 0) return 0;
     NSB_REQUIRE(meta && params_half && net && sdf && nablas && rgb && view_dirs, "nsb_fused_color_fwd: NULL argument");
     NSB_REQUIRE(x || (rays_o && rays_d && t), "nsb_fused_color_fwd: need x or (rays_o, rays_d, t)");
@@ -819,9 +820,11 @@ extern "C" int nsb_fused_color_fwd(const nsb_lotd_meta *meta, const void *params
     constexpr int kSmem = 2 * kTileBytes + 2 * HW * NF * 2 + 2 * XW * XW * 2 + 1024;
     cudaFuncSetAttribute(k_color_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     PointSrc ps{x, rays_o, rays_d, t, ridx};
+    OccCollect oc{nullptr, 1, 1, 1, 0.f};
+    if (collect && collect->grid_pcl) oc = OccCollect{collect->grid_pcl, collect->res[0], collect->res[1], collect->res[2], collect->inv_s};
     k_color_fwd<<<tiles_grid(n, 3), kTile, kSmem, (cudaStream_t)stream>>>(m, (const __half *)params_half, d, ps, view_dirs, h_appear, n,
                                                                           max_level < 0 ? -1 : max_level, sdf, nablas, rgb, x_out, (uint8_t *)act_z,
-                                                                          (uint8_t *)act_x, (uint8_t *)act_y1, (uint8_t *)act_y2);
+                                                                          (uint8_t *)act_x, (uint8_t *)act_y1, (uint8_t *)act_y2, oc);
     return check_launch("nsb_fused_color_fwd");
 }
 

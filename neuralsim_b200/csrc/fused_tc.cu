@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kTile)
 k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
                const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ridx,
                const float *__restrict__ t, int64_t n, int max_level, float *__restrict__ sdf, const int64_t *__restrict__ pack_infos,
-               const int64_t *__restrict__ pack_ray, int64_t n_packs) {
+               const int64_t *__restrict__ pack_ray, int64_t n_packs, const OccCollect oc) {
     __shared__ __align__(1024) uint8_t sA[kTile * NF * 2];   // 8 KB : features, chunk-major core-matrix layout
     __shared__ __align__(1024) uint8_t sB[HW * NF * 2];      // 4 KB : W1 [64 x 32], same layout
     __shared__ float sb1[HW], sW2[HW];
@@ -128,7 +128,10 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
 #pragma unroll
                 for (int q = 0; q < 3; ++q) xs[q] = fminf(fmaxf(__fmaf_rn(xs[q], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
                 const float v = sdf_of_tile<FAST_SP, UNROLL>(ctx, xs, tid, phase);
-                if (valid) sdf[first + k] = v;
+                if (valid) {
+                    sdf[first + k] = v;
+                    if (oc.pcl) occ_collect_point(oc, xs, v);
+                }
             }
         }
     } else {
@@ -139,7 +142,10 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
             float xs[3];
             load_point(MODE == 1, x, rays_o, rays_d, ridx, t, i, valid, xs);
             const float v = sdf_of_tile<FAST_SP, UNROLL>(ctx, xs, tid, phase);
-            if (valid) sdf[i] = v;
+            if (valid) {
+                sdf[i] = v;
+                if (oc.pcl) occ_collect_point(oc, xs, v);
+            }
         }
     }
     if (warp == 0) tc::tmem_free<64>(ctx.tmem);
@@ -331,22 +337,23 @@ static inline unsigned persistent_grid(int64_t n, int ctas_per_sm) {
 
 template <int MODE>
 static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta &m, const __half *g, const DecoderDevTC &d, const float *x, const float *ro,
-                       const float *rd, const int64_t *ridx, const float *t, int64_t n, int ml, float *sdf, const int64_t *pi, const int64_t *pr, int64_t np) {
+                       const float *rd, const int64_t *ridx, const float *t, int64_t n, int ml, float *sdf, const int64_t *pi, const int64_t *pr, int64_t np,
+                       const OccCollect &oc) {
     // ray-major order: libm softplus (its longer epilogue keeps fewer warps in the gather phase at once -> less L1 thrash);
     // ray-tiled order: SFU softplus (gathers coalesce, the kernel is issue-bound again).  profiles/r01e_ab.txt
     // variants: 0 libm / 2 levels per trip, 1 SFU / 2, 2 libm / 1, 3 SFU / 1
     if (variant < 0) variant = 1;                      // SFU softplus, two levels per trip: best in both orders (profiles/r01f_ab.txt)
-    if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
-    else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
-    else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
-    else k_fused_sdf_tc<MODE, false, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np);
+    if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
+    else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
+    else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
+    else k_fused_sdf_tc<MODE, false, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
 }
 
 // mode 0: x[n,3];  1: (rays_o, rays_d, ridx, t)[n];  2: ray-tiled packs (pack_infos[n_packs,2], pack_ray[n_packs] or NULL, t, sdf packed)
 extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *params_half, const nsb_sdf_decoder *dec, const float *x,
                                        const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
                                        int32_t max_level, float *sdf, void *stream, int mode, const int64_t *pack_infos,
-                                       const int64_t *pack_ray, int64_t n_packs) {
+                                       const int64_t *pack_ray, int64_t n_packs, const nsb_occ_collect *collect) {
     PLMeta m;
     if (make_plmeta(meta, &m)) return 2;
     NSB_REQUIRE(m.n_pseudo == 16 && m.F == 2 && m.D == 3 && plmeta_two_feature_cells(m), "nsb_fused_sdf (tensor-core): built for 16 x 2 LoTD features in 3-D");
@@ -359,11 +366,13 @@ extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *pa
     cudaStream_t s = (cudaStream_t)stream;
     const int ml = max_level < 0 ? -1 : max_level;
     const __half *g = (const __half *)params_half;
+    OccCollect oc{nullptr, 1, 1, 1, 0.f};
+    if (collect && collect->grid_pcl) oc = OccCollect{collect->grid_pcl, collect->res[0], collect->res[1], collect->res[2], collect->inv_s};
     if (mode == 2) {
         const int64_t groups = (n_packs + 31) / 32, wave = (int64_t)sm_count() * ctas;
-        launch_sdf<2>(variant, (unsigned)(groups < wave ? groups : wave), s, m, g, d, nullptr, rays_o, rays_d, nullptr, t, n, ml, sdf, pack_infos, pack_ray, n_packs);
-    } else if (mode == 1) launch_sdf<1>(variant, persistent_grid(n, ctas), s, m, g, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf, nullptr, nullptr, 0);
-    else launch_sdf<0>(variant, persistent_grid(n, ctas), s, m, g, d, x, nullptr, nullptr, nullptr, nullptr, n, ml, sdf, nullptr, nullptr, 0);
+        launch_sdf<2>(variant, (unsigned)(groups < wave ? groups : wave), s, m, g, d, nullptr, rays_o, rays_d, nullptr, t, n, ml, sdf, pack_infos, pack_ray, n_packs, oc);
+    } else if (mode == 1) launch_sdf<1>(variant, persistent_grid(n, ctas), s, m, g, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf, nullptr, nullptr, 0, oc);
+    else launch_sdf<0>(variant, persistent_grid(n, ctas), s, m, g, d, x, nullptr, nullptr, nullptr, nullptr, n, ml, sdf, nullptr, nullptr, 0, oc);
     return check_launch("nsb_fused_sdf(tc)");
 }
 

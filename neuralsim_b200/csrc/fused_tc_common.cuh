@@ -12,6 +12,25 @@ struct DecoderDevTC {
     float beta;
 };
 
+// accel.collect_samples fused into the query kernels (see nsb_occ_collect): xs is the point in [0,1]^3 table space (clamped: the
+// voxel index is the same as for the unclamped point), sdf the fp16-valued result.
+struct OccCollect {
+    float *pcl;
+    int rx, ry, rz;
+    float inv_s;
+};
+__device__ __forceinline__ float r16(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ void occ_collect_point(const OccCollect &oc, const float (&xs)[3], float sdf) {
+    const int ix = min(max((int)__fmul_rn(xs[0], (float)oc.rx), 0), oc.rx - 1);
+    const int iy = min(max((int)__fmul_rn(xs[1], (float)oc.ry), 0), oc.ry - 1);
+    const int iz = min(max((int)__fmul_rn(xs[2], (float)oc.rz), 0), oc.rz - 1);
+    // (1. / cosh((inv_s * x / 2.).clamp(-20, 20))) ** 2 on a half tensor: every op rounds to fp16 (maths/common.py:122-133)
+    const float a = fminf(fmaxf(r16(r16(__fmul_rn(sdf, oc.inv_s)) * 0.5f), -20.f), 20.f);
+    const float r = r16(__fdiv_rn(1.f, r16(coshf(a))));
+    const float v = r16(__fmul_rn(r, r));
+    if (v > 0.f) atomicMax(reinterpret_cast<int *>(oc.pcl) + ((ix * oc.ry + iy) * oc.rz + iz), __float_as_int(v));   // v >= 0: int order == float order
+}
+
 constexpr int kTile = 128;
 constexpr int NF = 32, HW = 64;           // features, hidden width (zero padded to 64)
 

@@ -3,6 +3,8 @@
 torch_scatter's `scatter_max(out=decay*grid)` is `Tensor.scatter_reduce_('amax', include_self=True)` here."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -23,9 +25,9 @@ def sample_pts_in_voxels(gidx, num_pts, resolution, dtype=torch.float, generator
 
 
 def sdf_to_occ_val(sdf, inv_s):
-    """normalised logistic density: 4 s (1 - s), s = sigmoid(sdf * inv_s)   (maths: normalized_logistic_density)."""
-    s = torch.sigmoid(sdf * inv_s)
-    return 4. * s * (1. - s)
+    """normalised logistic density with peak 1, as the reference writes it: (1 / cosh(clamp(inv_s x / 2, -20, 20)))^2
+    (nr3d_lib/maths/common.py:122-133), evaluated in the dtype of `sdf` (the reference's sdf is a half tensor)."""
+    return (1. / torch.cosh((inv_s * sdf / 2.).clamp_(-20, 20))) ** 2
 
 
 class OccGridEma(nn.Module):
@@ -51,7 +53,19 @@ class OccGridEma(nn.Module):
             self.register_buffer("_occ_val_grid_pcl", torch.zeros(res.tolist(), dtype=dtype, device=device), persistent=False)
 
     def occ_val_fn(self, sdf):
-        return sdf_to_occ_val(sdf.float(), self.occ_inv_s)
+        # the model's sdf is fp16-valued (autocast decoder): evaluate like the reference does on its half tensor, then widen
+        return sdf_to_occ_val(sdf.half(), self.occ_inv_s).float()
+
+    def collect_struct(self):
+        """nsb_occ_collect for the fused query kernels (None when samples are not collected): they max-accumulate the occupancy evidence
+        of every point they evaluate into `_occ_val_grid_pcl`, which is what `collect_samples(x, sdf)` does after the query."""
+        if not (self.training and self.should_collect_samples):
+            return None
+        from .. import _lib as L
+        g = self._occ_val_grid_pcl
+        c = L.OccCollectC(g.data_ptr(), (ctypes.c_int32 * 3)(*g.shape), float(self.occ_inv_s))
+        c._keep = g
+        return c
 
     def _ravel(self, gidx):
         r = self.occ_val_grid.shape

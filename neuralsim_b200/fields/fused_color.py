@@ -17,7 +17,7 @@ from .. import _lib as L
 
 class _FusedColor(autograd.Function):
     @staticmethod
-    def forward(ctx, model, pts, view_dirs, h_appear, max_level, keep, *params):
+    def forward(ctx, model, pts, view_dirs, h_appear, max_level, keep, collect, *params):
         grid16, net, _held = model._fused_color_state()
         ridx, t, rays_o, rays_d = pts
         n, dev = t.numel(), t.device
@@ -33,7 +33,8 @@ class _FusedColor(autograd.Function):
         with L.KERNEL_TIMER.time("fused_color_fwd", n):
             L.check(L.lib().nsb_fused_color_fwd(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(net), None, L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
                                                 L.ptr(ridx, "i64"), L.ptr(t, "f32"), L.ptr(view_dirs, "f32"), L.ptr(h_appear, "f32", allow_none=True),
-                                                L.c_i64(n), L.c_i32(max_level), L.ptr(sdf), L.ptr(nab), L.ptr(rgb), L.ptr(x), *ap, L.stream_ptr()),
+                                                L.c_i64(n), L.c_i32(max_level), L.ptr(sdf), L.ptr(nab), L.ptr(rgb), L.ptr(x), *ap,
+                                                ctypes.byref(collect) if collect is not None else None, L.stream_ptr()),
                     "fused_color_fwd")
         ctx.model, ctx.pts, ctx.max_level, ctx.n = model, pts, max_level, n
         ctx.held = (grid16, net, _held, acts, rgb)
@@ -58,7 +59,7 @@ class _FusedColor(autograd.Function):
             grads.append(small[o:o + k].view(sh))
             o += k
         if g_sdf is None and g_nab is None and g_rgb is None:
-            return (None,) * 6 + tuple(grads)
+            return (None,) * 7 + tuple(grads)
         ridx, t, rays_o, rays_d = ctx.pts
         c = lambda g: None if g is None else g.contiguous().float()
         g_sdf, g_nab, g_rgb = c(g_sdf), c(g_nab), c(g_rgb)
@@ -69,10 +70,10 @@ class _FusedColor(autograd.Function):
                                                 L.ptr(acts[2]), L.ptr(acts[3]), L.ptr(rgb), L.ptr(g_sdf, allow_none=True), L.ptr(g_nab, allow_none=True),
                                                 L.ptr(g_rgb, allow_none=True), L.ptr(dh), *[L.ptr(g) for g in grads], L.stream_ptr()),
                     "fused_color_bwd")
-        return (None,) * 6 + tuple(grads)
+        return (None,) * 7 + tuple(grads)
 
 
-def fused_color(model, ridx, t, rays_o, rays_d, view_dirs, h_appear=None, *, nablas_has_grad=True):
+def fused_color(model, ridx, t, rays_o, rays_d, view_dirs, h_appear=None, *, nablas_has_grad=True, collect=None):
     """-> dict(sdf [n], nablas [n,3], rgb [n,3], x [n,3]).  Gradients flow to the table, the decoder and the radiance net."""
     s, r = model.implicit_surface, model.radiance_net.blocks.layers
     d = s.decoder.layers
@@ -82,7 +83,7 @@ def fused_color(model, ridx, t, rays_o, rays_d, view_dirs, h_appear=None, *, nab
            rays_d.detach().contiguous().float())
     keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     ha = None if h_appear is None else h_appear.detach().contiguous().float()
-    sdf, nab, rgb, x = _FusedColor.apply(model, pts, view_dirs.detach().contiguous().float(), ha, s._ml(model.max_level), keep, *params)
+    sdf, nab, rgb, x = _FusedColor.apply(model, pts, view_dirs.detach().contiguous().float(), ha, s._ml(model.max_level), keep, collect, *params)
     if not nablas_has_grad:
         nab = nab.detach()
     return dict(sdf=sdf, nablas=nab, rgb=rgb, x=x)

@@ -142,26 +142,10 @@ class _FusedSDF(autograd.Function):
     @staticmethod
     def forward(ctx, owner, pts, max_level, grid, W1, b1, W2, b2):
         grid16, dec = owner._fused_state()
-        meta = owner.encoding.meta
-        if isinstance(pts, tuple):
-            ridx, t, rays_o, rays_d, packs = pts
-            n = t.numel()
-            sdf = torch.empty(n, dtype=torch.float32, device=t.device)
-            with L.KERNEL_TIMER.time("fused_sdf_fwd", n):
-                if packs is not None:          # coherent rays: ray-tiled traversal of the same packed samples
-                    L.check(L.lib().nsb_fused_sdf_packs(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
-                                                        L.ptr(packs[0], "i64"), L.ptr(packs[1], "i64", allow_none=True), L.c_i64(packs[0].shape[0]),
-                                                        L.ptr(t, "f32"), L.c_i32(max_level), L.ptr(sdf), L.stream_ptr()), "fused_sdf_packs")
-                else:
-                    L.check(L.lib().nsb_fused_sdf_rays(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
-                                                       L.ptr(ridx, "i64"), L.ptr(t, "f32"), L.c_i64(n), L.c_i32(max_level), L.ptr(sdf), L.stream_ptr()), "fused_sdf")
-        else:
-            n = pts.shape[0]
-            sdf = torch.empty(n, dtype=torch.float32, device=pts.device)
-            with L.KERNEL_TIMER.time("fused_sdf_fwd", n):
-                L.check(L.lib().nsb_fused_sdf(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(pts, "f32"), L.c_i64(n), L.c_i32(max_level),
-                                              L.ptr(sdf), None, L.stream_ptr()), "fused_sdf")
-        ctx.owner, ctx.pts, ctx.max_level, ctx.n = owner, pts, max_level, n
+        with L.KERNEL_TIMER.time("fused_sdf_fwd", (pts[1] if isinstance(pts, tuple) else pts).shape[0]):
+            sdf = owner._launch_sdf(grid16, dec, pts, max_level)
+        n = sdf.shape[0]
+        ctx.owner, ctx.pts, ctx.max_level, ctx.n = owner, pts[:5] if isinstance(pts, tuple) else pts, max_level, n
         ctx.held = (grid16, dec)          # the fp16 images the forward used
         ctx.shapes = (grid.shape, W1.shape, b1.shape, W2.shape, b2.shape)
         return sdf
@@ -188,7 +172,7 @@ class _FusedSDF(autograd.Function):
         if sparse:
             d_sdf = d_sdf[keep]
         if isinstance(ctx.pts, tuple):
-            ridx, t, rays_o, rays_d, _packs = ctx.pts
+            ridx, t, rays_o, rays_d, _packs = ctx.pts[:5]
             if sparse:
                 ridx, t = ridx[keep], t[keep]
             args = (None, L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"), L.ptr(ridx, "i64"), L.ptr(t, "f32"))
@@ -238,21 +222,47 @@ class LoTDSDF(nn.Module):
         ml = max_level or self.encoding.max_level
         return self.encoding.meta.n_levels if ml is None else int(ml)
 
-    def fused_sdf_autograd(self, x, max_level: int = None):
+    def _launch_sdf(self, grid16, dec, pts, max_level):
+        """one launch of the fused query.  pts: x [n,3]  |  (ridx, t, rays_o, rays_d, packs | None[, collect | None])"""
+        meta = self.encoding.meta
+        if isinstance(pts, tuple):
+            ridx, t, rays_o, rays_d, packs = pts[:5]
+            collect = pts[5] if len(pts) > 5 else None
+            sdf = torch.empty(t.numel(), dtype=torch.float32, device=t.device)
+            mode = 2 if packs is not None else 1
+            L.check(L.lib().nsb_fused_sdf_collect(
+                meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), None, L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
+                L.ptr(ridx, "i64", allow_none=(mode == 2)) if mode == 1 else None, L.ptr(t, "f32"), L.c_i64(t.numel()),
+                L.ptr(packs[0], "i64") if mode == 2 else None, L.ptr(packs[1], "i64", allow_none=True) if mode == 2 else None,
+                L.c_i64(packs[0].shape[0] if mode == 2 else 0), L.c_i32(mode), L.c_i32(max_level), L.ptr(sdf),
+                ctypes.byref(collect) if collect is not None else None, L.stream_ptr()), "fused_sdf")
+            return sdf
+        sdf = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
+        L.check(L.lib().nsb_fused_sdf_collect(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(pts, "f32"), None, None, None, None,
+                                              L.c_i64(pts.shape[0]), None, None, L.c_i64(0), L.c_i32(0), L.c_i32(max_level), L.ptr(sdf),
+                                              ctypes.byref(self._collect) if getattr(self, "_collect", None) is not None else None, L.stream_ptr()),
+                "fused_sdf")
+        return sdf
+
+    def fused_sdf_autograd(self, x, max_level: int = None, collect=None):
         """differentiable (wrt. table + decoder) fused query on points [...,3]"""
         d = self.decoder.layers
         prefix = x.shape[:-1]
-        sdf = _FusedSDF.apply(self, x.detach().reshape(-1, 3).contiguous().float(), self._ml(max_level), self.encoding.flattened_params,
-                              d[0].weight, d[0].bias, d[1].weight, d[1].bias)
+        self._collect = collect
+        try:
+            sdf = _FusedSDF.apply(self, x.detach().reshape(-1, 3).contiguous().float(), self._ml(max_level), self.encoding.flattened_params,
+                                  d[0].weight, d[0].bias, d[1].weight, d[1].bias)
+        finally:
+            self._collect = None
         return sdf.view(prefix)
 
-    def fused_sdf_rays_autograd(self, ridx, t, rays_o, rays_d, max_level: int = None, packs=None):
+    def fused_sdf_rays_autograd(self, ridx, t, rays_o, rays_d, max_level: int = None, packs=None, collect=None):
         d = self.decoder.layers
         shape = t.shape
         if t.dim() == 2:
             ridx = ridx.unsqueeze(-1).expand(shape)
         pts = (ridx.reshape(-1).contiguous().long(), t.detach().reshape(-1).contiguous().float(), rays_o.detach().contiguous(),
-               rays_d.detach().contiguous(), packs)
+               rays_d.detach().contiguous(), packs, collect)
         sdf = _FusedSDF.apply(self, pts, self._ml(max_level), self.encoding.flattened_params, d[0].weight, d[0].bias, d[1].weight, d[1].bias)
         return sdf.view(shape)
 
@@ -292,29 +302,29 @@ class LoTDSDF(nn.Module):
         return self._fused_cache[1][0], self._fused_cache[2]
 
     @torch.no_grad()
-    def fused_sdf(self, x, max_level: int = None):
+    def fused_sdf(self, x, max_level: int = None, collect=None):
         grid16, dec = self._fused_state()
         prefix = x.shape[:-1]
         xf = x.reshape(-1, 3).contiguous().float()
-        sdf = torch.empty(xf.shape[0], dtype=torch.float32, device=xf.device)
-        ml = self.encoding.meta.n_levels if (max_level or self.encoding.max_level) is None else int(max_level or self.encoding.max_level)
-        with L.KERNEL_TIMER.time("lotd_gather", xf.shape[0]):
-          L.check(L.lib().nsb_fused_sdf(self.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(xf, "f32"),
-                                      L.c_i64(xf.shape[0]), L.c_i32(ml), L.ptr(sdf), None, L.stream_ptr()), "fused_sdf")
+        self._collect = collect
+        try:
+            with L.KERNEL_TIMER.time("lotd_gather", xf.shape[0]):
+                sdf = self._launch_sdf(grid16, dec, xf, self._ml(max_level))
+        finally:
+            self._collect = None
         return sdf.view(prefix)
 
     @torch.no_grad()
-    def fused_sdf_rays(self, ridx, t, rays_o, rays_d, max_level: int = None, packs=None):
+    def fused_sdf_rays(self, ridx, t, rays_o, rays_d, max_level: int = None, packs=None, collect=None):
         grid16, dec = self._fused_state()
         shape = t.shape
-        if packs is not None:
+        if packs is not None or collect is not None:
+            if packs is None and t.dim() == 2:
+                ridx = ridx.unsqueeze(-1).expand(shape)
             tf = t.reshape(-1).contiguous().float()
-            sdf = torch.empty(tf.shape[0], dtype=torch.float32, device=tf.device)
-            ml = self.encoding.meta.n_levels if (max_level or self.encoding.max_level) is None else int(max_level or self.encoding.max_level)
+            pts = (ridx.reshape(-1).contiguous().long() if packs is None else None, tf, rays_o.contiguous(), rays_d.contiguous(), packs, collect)
             with L.KERNEL_TIMER.time("lotd_gather", tf.shape[0]):
-                L.check(L.lib().nsb_fused_sdf_packs(self.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o.contiguous(), "f32"),
-                                                    L.ptr(rays_d.contiguous(), "f32"), L.ptr(packs[0], "i64"), L.ptr(packs[1], "i64", allow_none=True),
-                                                    L.c_i64(packs[0].shape[0]), L.ptr(tf, "f32"), L.c_i32(ml), L.ptr(sdf), L.stream_ptr()), "fused_sdf_packs")
+                sdf = self._launch_sdf(grid16, dec, pts, self._ml(max_level))
             return sdf.view(shape)
         if t.dim() == 2:
             ridx = ridx.unsqueeze(-1).expand(shape)

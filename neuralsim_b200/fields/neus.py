@@ -65,15 +65,16 @@ class LoTDNeuS(nn.Module):
             return self.implicit_surface(x, return_h=True, max_level=self.max_level)
         return self.implicit_surface.forward_sdf(x, max_level=self.max_level)
 
-    def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d, packs=None):
+    def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d, packs=None, collect=None):
         """sdf at o[ridx] + d[ridx]*t.  No-grad calls never materialise the points (fused kernel).
         packs = (pack_infos [P,2], ray of every pack [P] | None): the samples are the packs of coherent (image-ordered) rays -> the
-        fused kernel walks them ray-tiled; same values."""
+        fused kernel walks them ray-tiled; same values.  collect = nsb_occ_collect | None: the accel's sample collection, done by the kernel."""
         if self.implicit_surface._fusable():
             if not torch.is_grad_enabled():
-                return dict(sdf=self.implicit_surface.fused_sdf_rays(ridx, t, rays_o, rays_d, max_level=self.max_level, packs=packs))
+                return dict(sdf=self.implicit_surface.fused_sdf_rays(ridx, t, rays_o, rays_d, max_level=self.max_level, packs=packs, collect=collect))
             if not (t.requires_grad or rays_o.requires_grad or rays_d.requires_grad):
-                return dict(sdf=self.implicit_surface.fused_sdf_rays_autograd(ridx, t, rays_o, rays_d, max_level=self.max_level, packs=packs))
+                return dict(sdf=self.implicit_surface.fused_sdf_rays_autograd(ridx, t, rays_o, rays_d, max_level=self.max_level, packs=packs,
+                                                                              collect=collect))
         if t.dim() == 2:
             x = torch.addcmul(rays_o[ridx].unsqueeze(-2), rays_d[ridx].unsqueeze(-2), t.unsqueeze(-1)).flatten(0, -2)
             return dict(sdf=self.forward_sdf(x)["sdf"].view(t.shape))
@@ -107,8 +108,10 @@ class LoTDNeuS(nn.Module):
 
     def forward_on_rays(self, ridx, t, rays_o, rays_d, view_dirs, rays_h_appear=None, *, nablas_has_grad=True):
         """LoTDNeuS.forward at x = o[ridx] + d[ridx] t with per-ray view_dirs / h_appear, as one fused op (fields/fused_color.py)."""
+        accel = getattr(self, "accel", None)
+        collect = accel.occ.collect_struct() if (self.training and accel is not None) else None
         return fused_color(self, ridx, t, rays_o, rays_d, view_dirs, rays_h_appear if self.use_h_appear else None,
-                           nablas_has_grad=nablas_has_grad)
+                           nablas_has_grad=nablas_has_grad, collect=collect)
 
     @torch.no_grad()
     def query_sdf(self, x):
@@ -158,19 +161,21 @@ class LoTDNeuSModel(LoTDNeuS):
 
     # ---- the accel watches every training-time SDF query (renderer_mixin.py:154-164)
     def forward_sdf(self, x, skip_accel=False, **kw):
+        collect = self.accel.occ.collect_struct() if (self.training and not skip_accel and self.accel is not None) else None
+        if collect is not None and not kw.get("return_h", False) and self.implicit_surface._fusable() and not x.requires_grad:
+            s = self.implicit_surface                               # the fused query collects in-kernel
+            fn = s.fused_sdf_autograd if torch.is_grad_enabled() else s.fused_sdf
+            return dict(sdf=fn(x, max_level=self.max_level, collect=collect))
         ret = super().forward_sdf(x, **kw)
         if self.training and not skip_accel and self.accel is not None:
             self.accel.collect_samples(x, val=ret["sdf"].detach())
         return ret
 
     def forward_sdf_on_rays(self, ridx, t, rays_o, rays_d, packs=None):
-        ret = super().forward_sdf_on_rays(ridx, t, rays_o, rays_d, packs=packs)
-        if self.training and self.accel is not None and self.accel.occ.should_collect_samples:
-            # the fused query never materialised the points; rebuild them only to feed the accel's statistics
-            r = ridx.unsqueeze(-1).expand(t.shape) if t.dim() == 2 else ridx
-            x = torch.addcmul(rays_o[r], rays_d[r], t.unsqueeze(-1))
-            self.accel.collect_samples(x, val=ret["sdf"].detach())
-        return ret
+        # training: the accel watches every SDF query (renderer_mixin.py:154-164).  The fused kernels do the collection themselves
+        # (nsb_occ_collect); the unfused fall-back went through self.forward_sdf, which collected already.
+        collect = self.accel.occ.collect_struct() if (self.training and self.accel is not None) else None
+        return super().forward_sdf_on_rays(ridx, t, rays_o, rays_d, packs=packs, collect=collect)
 
     def forward_sdf_nablas(self, x, skip_accel=False, **kw):
         ret = super().forward_sdf_nablas(x, **kw)

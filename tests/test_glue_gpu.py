@@ -219,3 +219,45 @@ def test_ray_test_flags_image_ordered_rays(cuda):
     assert sp.ray_test(ro.cuda(), rd.cuda(), near=0.01)["rays_coherent"] is True
     perm = torch.randperm(ro.shape[0])
     assert sp.ray_test(ro[perm].cuda(), rd[perm].cuda(), near=0.01)["rays_coherent"] is False
+
+
+def test_in_kernel_sample_collection_equals_collect_samples(cuda):
+    """nsb_occ_collect: the occupancy evidence the query kernels accumulate == OccGridEma.collect_samples(x, sdf) on the same sdf."""
+    from util import make_pair
+    from neuralsim_b200.fields import LoTDNeuSModel
+    P, model0 = make_pair(cuda)
+    model = LoTDNeuSModel(surface_cfg=dict(bounding_size=2.0, encoding_cfg=dict(lotd_cfg=P.lotd_cfg)), radiance_cfg=dict(n_appear_embedding=P.n_appear),
+                          accel_cfg=dict(resolution=[64, 64, 64], update_from_samples_cfg=dict()), device=cuda)
+    model.load_state_dict(model0.state_dict(), strict=False)
+    model.train()
+    occ = model.accel.occ
+    assert occ.should_collect_samples and occ.collect_struct() is not None
+    g = torch.Generator().manual_seed(21)
+    x = (torch.rand(200_000, 3, generator=g) * 2 - 1).cuda()
+    x[:1000] = (torch.rand(1000, 3, generator=g).cuda() - 0.5) * 1.02        # a cluster around the sphere-like surface region
+    x[0] = torch.tensor([1.0, -1.0, 1.0])                                   # corners of the box: index clamping
+    with torch.no_grad():
+        sdf = model.forward_sdf(x)["sdf"]                                    # fused query, collects in-kernel
+    got = occ._occ_val_grid_pcl.clone()
+    occ._occ_val_grid_pcl.zero_()
+    occ.collect_samples(x, val=sdf)                                          # the torch restatement of the reference (accel.py)
+    ref = occ._occ_val_grid_pcl.clone()
+    assert float(ref.max()) > 0.5 and torch.equal(got, ref)
+    # ray-parameterised queries (ray-major and ray-tiled) collect the same evidence as their materialised points
+    R = 300
+    ro = (torch.tensor([-2.5, 0., 0.]) + 0.1 * torch.randn(R, 3, generator=g)).cuda()
+    rd = torch.nn.functional.normalize(torch.tensor([1., 0., 0.]) + 0.2 * torch.randn(R, 3, generator=g), dim=-1).cuda()
+    t = (1.6 + 1.8 * torch.rand(R, 40, generator=g)).sort(-1).values.cuda()
+    ridx = torch.arange(R, device=cuda)
+    pts = torch.addcmul(ro[:, None, :], rd[:, None, :], t[..., None]).reshape(-1, 3)
+    grids = []
+    for packs in (None, (torch.stack([ridx * 40, torch.full_like(ridx, 40)], 1).contiguous(), None)):
+        occ._occ_val_grid_pcl.zero_()
+        with torch.no_grad():
+            s = model.forward_sdf_on_rays(ridx, t, ro, rd, packs=packs)["sdf"]
+        grids.append(occ._occ_val_grid_pcl.clone())
+    occ._occ_val_grid_pcl.zero_()
+    occ.collect_samples(pts, val=s.reshape(-1))
+    assert torch.equal(grids[0], grids[1]) and torch.equal(grids[0], occ._occ_val_grid_pcl)
+    model.eval()
+    assert occ.collect_struct() is None
