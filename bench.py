@@ -124,7 +124,8 @@ class ClockSampler:
     Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_ms=100):
+        self.period_ms = period_ms
         self.index, self.proc, self.t0, self.t1 = index, None, None, None
         self.samples, self.reasons, self.max_mhz, self.n_all = [], set(), None, 0
 
@@ -142,8 +143,10 @@ class ClockSampler:
     def __enter__(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         phys = vis.split(",")[self.index].strip() if vis and len(vis.split(",")) > self.index else str(self.index)
+        if self.period_ms <= 0:
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", phys],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms), "-i", phys],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.first = self.proc.stdout.readline()     # block until its (slow, driver-heavy) start-up is over: it must not overlap the timed loops
         except Exception:
@@ -262,6 +265,7 @@ def main():
     ap.add_argument("--random-rays", action="store_true", help="draw the --rays rays of every pose as random pixels (a training batch) instead of the first rows")
     ap.add_argument("--collect-samples", action="store_true", help="accel.update_from_samples_cfg = {} as in the shipped training config: every "
                     "training-time SDF query also feeds the occupancy grid's evidence buffer (in-kernel here, torch_scatter in the reference)")
+    ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi loop period of the clock sampler; 0 = no sampler (diagnostics)")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
@@ -343,7 +347,7 @@ def main():
         loss_host.copy_(step(o, d), non_blocking=True)                                # D2H of the step's result
         torch.cuda.current_stream().synchronize()
 
-    with ClockSampler(local) as clocks:          # one looping nvidia-smi, forked before the warm-up; samples are attributed by timestamp
+    with ClockSampler(local, args.clock_period_ms) as clocks:          # one looping nvidia-smi, forked before the warm-up; samples are attributed by timestamp
         for i in range(args.warmup):
             resident(i)
         torch.cuda.synchronize()
