@@ -168,7 +168,7 @@ class ClockSampler:
             f = [x.strip() for x in line.split(",")]
             try:
                 ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(f[1]), float(f[2]), f[3:7]))
+                rows.append((ts, float(f[1]), float(f[2]) if len(f) > 2 else 0., f[3:7]))
             except Exception:
                 continue
         self.n_all = len(rows)
@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--collect-samples", action="store_true", help="accel.update_from_samples_cfg = {} as in the shipped training config: every "
                     "training-time SDF query also feeds the occupancy grid's evidence buffer (in-kernel here, torch_scatter in the reference)")
     ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi loop period of the clock sampler; 0 = no sampler (diagnostics)")
+    ap.add_argument("--clock-fields", default=None, help="override the sampler's --query-gpu field list (diagnostics)")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
@@ -347,6 +348,8 @@ def main():
         loss_host.copy_(step(o, d), non_blocking=True)                                # D2H of the step's result
         torch.cuda.current_stream().synchronize()
 
+    if args.clock_fields:
+        ClockSampler.Q = "timestamp," + args.clock_fields
     with ClockSampler(local, args.clock_period_ms) as clocks:          # one looping nvidia-smi, forked before the warm-up; samples are attributed by timestamp
         for i in range(args.warmup):
             resident(i)
