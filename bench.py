@@ -117,75 +117,71 @@ def loss_of(rendered):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region: ONE looping `nvidia-smi -lms 100` (the recipe of B200_PROFILING.md), forked
-    before the warm-up and read after the timed loops -- nothing is forked or queried from this process while the clock runs.
-    (An in-process NVML poll every 25 ms, and a thread forking nvidia-smi, both stalled the CUDA driver: 15 ms steps measured 50-230 ms.)
-    Samples are attributed to the timed region by nvidia-smi's own timestamps."""
-    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons during the timed region.
+
+    Measured on this pool (profiles/diag_clock_sampler.sh, /tmp logs of round 1): ANY concurrent poller -- a looping `nvidia-smi -lms 100..1000`,
+    a thread forking nvidia-smi, an NVML thread -- makes 7 of 8 runs of this launch- and sync-heavy step show 80-230 ms stalls inside 15 ms steps
+    (the driver serialises NVML queries with our launches); with no poller every step is 14.2-15.8 ms.  So the samples are taken IN-PROCESS through
+    NVML, synchronously from the timing loop, right after a step's closing event is recorded and before the next step's opening event: the GPU is
+    still executing the step just enqueued (the resident loop does not synchronise), nothing of ours is launching, and the query's cost falls outside
+    the per-step event pairs exactly like the L2 flush does.  Fallback without pynvml: one `nvidia-smi` call before and after the timed loops."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0, period_ms=100):
-        self.period_ms = period_ms
-        self.index, self.proc, self.t0, self.t1 = index, None, None, None
-        self.samples, self.reasons, self.max_mhz, self.n_all = [], set(), None, 0
-
-    @property
-    def armed(self):
-        return self.t0 is not None and self.t1 is None
-
-    @armed.setter
-    def armed(self, on):
-        if on:
-            self.t0, self.t1 = time.time(), None
-        else:
-            self.t1 = time.time()
+        self.index, self.enabled = index, period_ms > 0
+        self.samples, self.reasons, self.max_mhz, self.how = [], set(), None, None
+        self.nv = self.h = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.phys = vis.split(",")[index].strip() if vis and len(vis.split(",")) > index else str(index)
+        if self.enabled:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(int(self.phys)) if self.phys.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(self.phys)
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                self.nv, self.how = pynvml, "NVML, in-process, between the per-step event pairs of the timed loops"
+            except Exception:
+                self.nv = None
 
     def __enter__(self):
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = vis.split(",")[self.index].strip() if vis and len(vis.split(",")) > self.index else str(self.index)
-        if self.period_ms <= 0:
-            return self
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms), "-i", phys],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
-            self.first = self.proc.stdout.readline()     # block until its (slow, driver-heavy) start-up is over: it must not overlap the timed loops
-        except Exception:
-            self.proc = None
+        if self.enabled and self.nv is None:
+            self._smi()
         return self
 
     def __exit__(self, *a):
-        if self.proc is None:
-            return
-        time.sleep(0.12)                       # let the sample that covers the end of the region be printed
-        self.proc.terminate()
+        if self.enabled and self.nv is None:
+            self._smi()
+
+    def _smi(self):
         try:
-            out = getattr(self, "first", "") + self.proc.communicate(timeout=5)[0]
-        except Exception:
-            out = ""
-        import datetime
-        rows = []
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            try:
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(f[1]), float(f[2]) if len(f) > 2 else 0., f[3:7]))
-            except Exception:
-                continue
-        self.n_all = len(rows)
-        t0, t1 = (self.t0 or 0.) - 0.1, (self.t1 or time.time()) + 0.1
-        inside = [r for r in rows if t0 <= r[0] <= t1] or rows[-2:]
-        for ts, mhz, mx, flags in inside:
-            self.samples.append(mhz)
-            self.max_mhz = mx
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", self.phys], capture_output=True, text=True,
+                                 timeout=10).stdout.strip().split(",")
+            self.samples.append(float(out[0])); self.max_mhz = float(out[1]); self.how = "nvidia-smi once before and once after the timed loops (no pynvml)"
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
                 if "Active" in v and "Not" not in v:
                     self.reasons.add(name)
+        except Exception:
+            pass
+
+    def sample(self):
+        """called by the timing loop between two steps"""
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples_in_timed_region": len(self.samples), "samples_total": self.n_all, "how": "nvidia-smi -lms 100, started before warm-up"}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no sampler"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "how": self.how}
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline / reference arm
@@ -265,8 +261,7 @@ def main():
     ap.add_argument("--random-rays", action="store_true", help="draw the --rays rays of every pose as random pixels (a training batch) instead of the first rows")
     ap.add_argument("--collect-samples", action="store_true", help="accel.update_from_samples_cfg = {} as in the shipped training config: every "
                     "training-time SDF query also feeds the occupancy grid's evidence buffer (in-kernel here, torch_scatter in the reference)")
-    ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi loop period of the clock sampler; 0 = no sampler (diagnostics)")
-    ap.add_argument("--clock-fields", default=None, help="override the sampler's --query-gpu field list (diagnostics)")
+    ap.add_argument("--clock-period-ms", type=int, default=100, help="0 = no clock sampler (diagnostics); any other value: sample between steps")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
@@ -323,13 +318,15 @@ def main():
             dist.all_reduce(flat)            # the one collective of a step: sum of the flat gradient
         return total
 
-    def timed(fn, k):
+    def timed(fn, k, sampler=None):
         evs = []
         for i in range(k):
             flush_buf.fill_(i & 0xff)         # L2 flush, outside the event pair
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(i); b.record()
             evs.append((a, b))
+            if sampler is not None:
+                sampler.sample()             # outside the event pair, while the GPU still runs the step just enqueued
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
@@ -348,9 +345,7 @@ def main():
         loss_host.copy_(step(o, d), non_blocking=True)                                # D2H of the step's result
         torch.cuda.current_stream().synchronize()
 
-    if args.clock_fields:
-        ClockSampler.Q = "timestamp," + args.clock_fields
-    with ClockSampler(local, args.clock_period_ms) as clocks:          # one looping nvidia-smi, forked before the warm-up; samples are attributed by timestamp
+    with ClockSampler(local, args.clock_period_ms) as clocks:          # see the class: NVML queries between the per-step event pairs
         for i in range(args.warmup):
             resident(i)
         torch.cuda.synchronize()
@@ -360,13 +355,11 @@ def main():
         import gc
         gc.collect()
         gc.disable()                           # no collector pause inside a 15 ms step; re-enabled right after the timed loops
-        clocks.armed = True
-        t_res = timed(resident, args.steps)
+        t_res = timed(resident, args.steps, clocks)
         launches = _lib.launch_count() - launches0
         if world > 1:
             dist.barrier()
-        t_e2e = timed(e2e, args.steps)
-        clocks.armed = False
+        t_e2e = timed(e2e, args.steps, clocks)
         gc.enable()
         # a separate, instrumented pass for the roofline: CUDA events around every launch of our kernels (not part of `value`)
         _lib.KERNEL_TIMER.enable()
