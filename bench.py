@@ -121,10 +121,10 @@ class ClockSampler:
 
     Measured on this pool (profiles/diag_clock_sampler.sh, /tmp logs of round 1): ANY concurrent poller -- a looping `nvidia-smi -lms 100..1000`,
     a thread forking nvidia-smi, an NVML thread -- makes 7 of 8 runs of this launch- and sync-heavy step show 80-230 ms stalls inside 15 ms steps
-    (the driver serialises NVML queries with our launches); with no poller every step is 14.2-15.8 ms.  So the samples are taken IN-PROCESS through
-    NVML, synchronously from the timing loop, right after a step's closing event is recorded and before the next step's opening event: the GPU is
-    still executing the step just enqueued (the resident loop does not synchronise), nothing of ours is launching, and the query's cost falls outside
-    the per-step event pairs exactly like the L2 flush does.  Fallback without pynvml: one `nvidia-smi` call before and after the timed loops."""
+    (NVML queries disturb CUDA submission for ~100 ms; even a query made between two steps shows up in the next ones, profiles/diag_*.sh); with no
+    poller every step is 14.2-15.8 ms.  So the samples are taken IN-PROCESS through NVML at the one moment they cannot perturb the measurement and are
+    still "during" it: right after the LAST step of the resident loop has been enqueued -- the GPU is then executing the timed steps (the loop does
+    not synchronise in between), and nothing of ours is left to launch.  Fallback without pynvml: one `nvidia-smi` call before and after."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -140,7 +140,7 @@ class ClockSampler:
                 pynvml.nvmlInit()
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(int(self.phys)) if self.phys.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(self.phys)
                 self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-                self.nv, self.how = pynvml, "NVML, in-process, between the per-step event pairs of the timed loops"
+                self.nv, self.how = pynvml, "NVML, in-process, while the GPU executes the enqueued timed steps (after the last launch of the resident loop)"
             except Exception:
                 self.nv = None
 
@@ -184,12 +184,25 @@ class ClockSampler:
                 "how": self.how}
 
 
+def effective_cpus():
+    """host cores this container may actually use: min(visible cores, cgroup CPU-bandwidth quota) -- the GPU boxes of this pool show 128
+    cores under a 16-CPU quota; 128 busy threads there are throttled for most of every 100 ms period."""
+    n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 # ---------------------------------------------------------------------------------------------- CPU baseline / reference arm
 def cpu_baseline(sample_rays=1536, threads=None):
     """The reference algorithm's CPU implementation (oracle port of nr3d_lib's path) on a bounded sample of the same workload:
     `sample_rays` rays of the 800x600 frame (strided over the image), fwd+bwd.  Runs on the host cores."""
     from oracle import render as orender, scene as oscene
-    threads = threads or os.cpu_count()
+    threads = threads or effective_cpus()
     torch.set_num_threads(threads)
     P = oscene.make_sphere_params()
     occ = oscene.make_occ_grid()
@@ -220,7 +233,7 @@ def run_reference(args, rank):
             times.append(rays / r["value"] / 1e6)
     ms = 1e3 * float(np.mean(times))
     val = rays / (ms / 1e3) / 1e6
-    base = dict(value=val, unit="Mrays/s", cores=os.cpu_count(), kind="port",
+    base = dict(value=val, unit="Mrays/s", cores=effective_cpus(), kind="port",
                 sample=f"{rays} rays of the 800x600 frame per step (bounded sample), fwd+bwd, oracle port of the reference path")
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/sec fwd+bwd", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
@@ -277,6 +290,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    torch.set_num_threads(max(1, min(8, effective_cpus())))      # host side of the GPU arm is one launching thread; keep the intra-op pool small
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
@@ -325,8 +339,9 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(i); b.record()
             evs.append((a, b))
-            if sampler is not None:
-                sampler.sample()             # outside the event pair, while the GPU still runs the step just enqueued
+        if sampler is not None:              # every step is enqueued and the GPU is still executing them: sample now, then drain
+            sampler.sample()
+            sampler.sample()
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
@@ -359,7 +374,8 @@ def main():
         launches = _lib.launch_count() - launches0
         if world > 1:
             dist.barrier()
-        t_e2e = timed(e2e, args.steps, clocks)
+        time.sleep(0.3)                      # NVML queries disturb CUDA submission for ~100 ms on this pool (see ClockSampler)
+        t_e2e = timed(e2e, args.steps)
         gc.enable()
         # a separate, instrumented pass for the roofline: CUDA events around every launch of our kernels (not part of `value`)
         _lib.KERNEL_TIMER.enable()
