@@ -256,9 +256,12 @@ int nsb_composite_backward(const float *alpha, const float *t, const float *rgb,
  *   pack_ops.py:286-291): first[n] = exclusive prefix sum of counts; info2[n,2] = (first, count) int32 (`packed_info`);
  *   for the non-zero entries in order: nz_index[j] = i, nz_pack[j] = (first_i, count_i), nz_src[j] = src[i];
  *   totals[2] = (sum of counts, number of non-zero entries), on the device.  Outputs other than totals may be NULL.
- *   workspace_zeroed: nsb_scan_workspace_bytes() of device memory, zero-filled before every call. */
+ *   workspace_zeroed: nsb_scan_workspace_bytes() of device memory, zero-filled before every call.
+ *   Host hand-off without a driver call: `totals` may point to mapped pinned host memory of >= 4 int64; with ticket != 0 the kernel
+ *   writes totals[2] = *extra_src (if given) and, after a system-scope fence, totals[3] = ticket, which the host polls. */
 int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first, int32_t *info2, int64_t *nz_index, int64_t *nz_pack,
-                    const int64_t *src, int64_t *nz_src, int64_t *totals, void *workspace_zeroed, void *stream);
+                    const int64_t *src, int64_t *nz_src, int64_t *totals, const int64_t *extra_src, int64_t ticket,
+                    void *workspace_zeroed, void *stream);
 /* bytes of the zero-filled device workspace nsb_scan_counts needs (inter-block totals + ready flags of its one-launch scan) */
 int64_t nsb_scan_workspace_bytes(void);
 /* merge_two_packs_sorted_aligned (pack_ops.py:529-560) fused with the scatter of the payloads: packs of (dep_a, sdf_a) and rows

@@ -60,7 +60,7 @@ __device__ __forceinline__ void block_scan_pair(int64_t &ps, int32_t &pz, int la
 __global__ void __launch_bounds__(kScanT)
 k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int64_t seg, ScanWs *__restrict__ ws, int32_t *__restrict__ first,
               int32_t *__restrict__ info2, int64_t *__restrict__ nz_index, int64_t *__restrict__ nz_pack, const int64_t *__restrict__ src,
-              int64_t *__restrict__ nz_src, int64_t *__restrict__ totals) {
+              int64_t *__restrict__ nz_src, int64_t *totals, const int64_t *__restrict__ extra_src, int64_t ticket) {
     __shared__ int64_t s_sum[32];
     __shared__ int32_t s_nz[32];
     __shared__ int64_t s_carry_sum;
@@ -94,7 +94,17 @@ k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int64_t seg, ScanWs
     __syncthreads();
     int64_t carry_sum = s_carry_sum;
     int32_t carry_nz = s_carry_nz;
-    if (b == gridDim.x - 1 && tid == 0) { totals[0] = carry_sum + my_sum; totals[1] = carry_nz + my_nz; }
+    if (b == gridDim.x - 1 && tid == 0) {
+        // `totals` may be mapped pinned host memory that the host polls (no driver call on its side): values first, then the ticket
+        volatile int64_t *tv = totals;
+        tv[0] = carry_sum + my_sum;
+        tv[1] = carry_nz + my_nz;
+        if (extra_src) tv[2] = extra_src[0];
+        if (ticket) {
+            __threadfence_system();
+            tv[3] = ticket;
+        }
+    }
     // ---- (3) scan my segment, kScanI consecutive items per thread and sweep
     for (int64_t base = lo; base < hi; base += (int64_t)kScanT * kScanI) {
         const int64_t i0 = base + (int64_t)tid * kScanI;
@@ -366,7 +376,8 @@ using namespace nsb;
 extern "C" int64_t nsb_scan_workspace_bytes(void) { return (int64_t)sizeof(ScanWs); }
 
 extern "C" int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first, int32_t *info2, int64_t *nz_index, int64_t *nz_pack,
-                               const int64_t *src, int64_t *nz_src, int64_t *totals, void *workspace_zeroed, void *stream) {
+                               const int64_t *src, int64_t *nz_src, int64_t *totals, const int64_t *extra_src, int64_t ticket,
+                               void *workspace_zeroed, void *stream) {
     NSB_REQUIRE(totals && workspace_zeroed, "nsb_scan_counts: totals / workspace is NULL");
     NSB_REQUIRE(n == 0 || counts, "nsb_scan_counts: counts is NULL");
     NSB_REQUIRE(!nz_src || src, "nsb_scan_counts: nz_src needs src");
@@ -376,7 +387,7 @@ extern "C" int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first,
     if (nb < 1) nb = 1;
     int64_t seg = (n + nb - 1) / nb;
     seg = (seg + kScanI - 1) / kScanI * kScanI;
-    k_scan_counts<<<(unsigned)nb, kScanT, 0, STREAM>>>(counts, n, seg, (ScanWs *)workspace_zeroed, first, info2, nz_index, nz_pack, src, nz_src, totals);
+    k_scan_counts<<<(unsigned)nb, kScanT, 0, STREAM>>>(counts, n, seg, (ScanWs *)workspace_zeroed, first, info2, nz_index, nz_pack, src, nz_src, totals, extra_src, ticket);
     return check_launch("nsb_scan_counts");
 }
 

@@ -164,7 +164,8 @@ class _FusedSDF(autograd.Function):
         d_sdf = d_sdf.contiguous().float()
         # Most boundary points of a NeuS ray carry an exactly-zero cotangent (saturated sigmoid far from the surface, samples
         # behind the early-stop): only the others are recomputed (the reference's scatter kernel skips them one by one).
-        keep = d_sdf.nonzero().squeeze(-1)
+        from ..graphics.neus_fused import scan_counts      # compaction without a driver-level sync (the size is polled from pinned memory)
+        keep = scan_counts(d_sdf.ne(0).to(torch.int32), want_index=True)["index"]
         n = keep.numel()
         if n == 0:
             return None, None, None, d_grid, d_W1, d_b1, d_W2, d_b2

@@ -100,7 +100,11 @@ class LoTDNeuS(nn.Module):
         cache = getattr(self, "_color_cache", None)
         if cache is None or cache[0] != key:
             t = [p.detach().to(torch.half).contiguous() for p in ps]
-            fac = (s.sdf_scale / s.radius3d_original).float().tolist()
+            r3 = s.radius3d_original                      # a buffer: read back once, not at every parameter update (a host sync)
+            fk = (r3.data_ptr(), r3._version, float(s.sdf_scale))
+            if getattr(self, "_fac_cache", (None,))[0] != fk:
+                self._fac_cache = (fk, (s.sdf_scale / r3).float().tolist())
+            fac = self._fac_cache[1]
             net = L.ColorNetC(*[x.data_ptr() for x in t], s.decoder.layers[0].out_features, b[0].out_features, b[0].in_features,
                               b[0].in_features - 54, float(s.decoder.layers[0].activation.beta), (ctypes.c_float * 3)(*fac))
             cache = self._color_cache = (key, t, net)

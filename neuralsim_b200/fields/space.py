@@ -77,12 +77,12 @@ class AABBSpace(nn.Module):
         o_n, d_n = torch.empty(R, 3, device=dev), torch.empty(R, 3, device=dev)
         nr, fr = torch.empty(R, device=dev), torch.empty(R, device=dev)
         flag = torch.empty(R, dtype=torch.int32, device=dev)
-        totals = torch.zeros(3, dtype=torch.int64, device=dev)
+        pairs = torch.zeros(1, dtype=torch.int64, device=dev)
         L.check(L.lib().nsb_ray_test_aabb(L.ptr(rays_o.contiguous(), "f32"), L.ptr(rays_d.contiguous(), "f32"), L.c_i64(R), c3, r3,
                                           ctypes.c_int(0 if near is None else 1), L.c_f32(0. if near is None else near),
                                           ctypes.c_int(0 if far is None else 1), L.c_f32(0. if far is None else far), L.ptr(o_n), L.ptr(d_n),
-                                          L.ptr(nr), L.ptr(fr), L.ptr(flag), ctypes.c_void_p(totals.data_ptr() + 16), L.stream_ptr()), "ray_test_aabb")
-        sc = scan_counts(flag, want_index=True, totals=totals)
+                                          L.ptr(nr), L.ptr(fr), L.ptr(flag), L.ptr(pairs), L.stream_ptr()), "ray_test_aabb")
+        sc = scan_counts(flag, want_index=True, extra=pairs)
         n, ridx = sc["n_nonzero"], sc["index"]
         o_c, d_c = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
         n_c, f_c = torch.empty(n, device=dev), torch.empty(n, device=dev)

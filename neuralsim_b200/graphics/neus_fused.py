@@ -110,6 +110,18 @@ class _GatherUnique(torch.autograd.Function):
 
 
 _SCAN_WS = []
+_HOST_SLOTS = {}
+
+
+def _host_slot():
+    """(pinned int64[4] tensor, its numpy view, ticket counter) -- the scan kernel writes the two totals (+ one extra) and a ticket there and
+    the host polls the ticket: a data-dependent size reaches Python without cudaMemcpy / cudaStreamSynchronize."""
+    dev = torch.cuda.current_device()
+    st = _HOST_SLOTS.get(dev)
+    if st is None:
+        t = torch.zeros(4, dtype=torch.int64).pin_memory()
+        st = _HOST_SLOTS[dev] = [t, t.numpy(), 0]
+    return st
 
 
 def _scan_ws_bytes():
@@ -120,7 +132,7 @@ def _scan_ws_bytes():
 
 
 @torch.no_grad()
-def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False, want_pack=False, src=None, totals=None):
+def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False, want_pack=False, src=None, extra=None):
     """One launch + ONE host read: exclusive scan of int32 counts and compaction of the non-zero entries.
     -> dict(total, n_nonzero, first?, info2?, index?, pack?, src?) with the compacted outputs already sliced."""
     n, dev = counts.shape[0], counts.device
@@ -129,15 +141,24 @@ def scan_counts(counts, *, want_first=False, want_info2=False, want_index=False,
     index = torch.empty(n, dtype=torch.int64, device=dev) if want_index else None
     pack = torch.empty(n, 2, dtype=torch.int64, device=dev) if want_pack else None
     nz_src = torch.empty(n, dtype=torch.int64, device=dev) if src is not None else None
-    if totals is None:               # else: a caller-owned int64[>=2] whose further slots another kernel filled; read in the same sync
-        totals = torch.empty(2, dtype=torch.int64, device=dev)
+    slot = _host_slot()
+    slot[2] += 1
+    ticket = slot[2]
     ws = torch.zeros(_scan_ws_bytes(), dtype=torch.uint8, device=dev)
     L.check(L.lib().nsb_scan_counts(L.ptr(counts, "i32"), L.c_i64(n), L.ptr(first, allow_none=True), L.ptr(info2, allow_none=True),
                                     L.ptr(index, allow_none=True), L.ptr(pack, allow_none=True), L.ptr(src, "i64", allow_none=True),
-                                    L.ptr(nz_src, allow_none=True), L.ptr(totals), L.ptr(ws), L.stream_ptr()), "scan_counts")
-    host = totals.tolist()                            # the one host sync: output sizes are data dependent
-    total, nnz = host[0], host[1]
-    out = dict(total=int(total), n_nonzero=int(nnz), first=first, info2=info2, extra=host[2:])
+                                    L.ptr(nz_src, allow_none=True), ctypes.c_void_p(slot[0].data_ptr()), L.ptr(extra, "i64", allow_none=True),
+                                    L.c_i64(ticket), L.ptr(ws), L.stream_ptr()), "scan_counts")
+    host = slot[1]                                    # the one host wait: output sizes are data dependent.  Polling pinned memory, no driver call
+    spins = 0
+    while host[3] != ticket:
+        spins += 1
+        if spins > 2_000_000 and spins % 1_000_000 == 0:     # ~ seconds: surface a dead kernel instead of hanging
+            torch.cuda.current_stream().synchronize()
+            if host[3] != ticket:
+                raise RuntimeError("scan_counts: the kernel finished without publishing its totals")
+    total, nnz = int(host[0]), int(host[1])
+    out = dict(total=total, n_nonzero=nnz, first=first, info2=info2, extra=[int(host[2])])
     out["index"] = index[:nnz] if index is not None else None
     out["pack"] = pack[:nnz] if pack is not None else None
     out["src"] = nz_src[:nnz] if nz_src is not None else None
