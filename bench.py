@@ -122,57 +122,35 @@ class ClockSampler:
     Measured on this pool (profiles/diag_clock_sampler.sh, /tmp logs of round 1): ANY concurrent poller -- a looping `nvidia-smi -lms 100..1000`,
     a thread forking nvidia-smi, an NVML thread -- makes 7 of 8 runs of this launch- and sync-heavy step show 80-230 ms stalls inside 15 ms steps
     (NVML queries disturb CUDA submission for ~100 ms; even a query made between two steps shows up in the next ones, profiles/diag_*.sh); with no
-    poller every step is 14.2-15.8 ms.  So the samples are taken IN-PROCESS through NVML at the one moment they cannot perturb the measurement and are
-    still "during" it: right after the LAST step of the resident loop has been enqueued -- the GPU is then executing the timed steps (the loop does
-    not synchronise in between), and nothing of ours is left to launch.  Fallback without pynvml: one `nvidia-smi` call before and after."""
-    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+    poller -- and no NVML session inside this process -- steps are 14.2-15.8 ms.  So ONE sample is taken, by a separate one-shot `nvidia-smi`
+    process, at the one moment it cannot perturb the measurement and is still "during" it: right after the LAST step of the resident loop has been
+    enqueued -- the GPU is then executing the timed steps and nothing of ours is left to launch."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0, period_ms=100):
         self.index, self.enabled = index, period_ms > 0
         self.samples, self.reasons, self.max_mhz, self.how = [], set(), None, None
-        self.nv = self.h = None
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         self.phys = vis.split(",")[index].strip() if vis and len(vis.split(",")) > index else str(index)
-        if self.enabled:
-            try:
-                import pynvml
-                pynvml.nvmlInit()
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(int(self.phys)) if self.phys.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(self.phys)
-                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-                self.nv, self.how = pynvml, "NVML, in-process, while the GPU executes the enqueued timed steps (after the last launch of the resident loop)"
-            except Exception:
-                self.nv = None
 
     def __enter__(self):
-        if self.enabled and self.nv is None:
-            self._smi()
         return self
 
     def __exit__(self, *a):
-        if self.enabled and self.nv is None:
-            self._smi()
+        pass
 
-    def _smi(self):
+    def sample(self):
+        """ONE `nvidia-smi` query (a separate process; nothing NVML-related ever lives in this one), called by the timing loop once the
+        last resident step has been enqueued: the GPU is executing the timed steps, and nothing of ours is left to launch."""
+        if not self.enabled:
+            return
         try:
             out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", self.phys], capture_output=True, text=True,
                                  timeout=10).stdout.strip().split(",")
-            self.samples.append(float(out[0])); self.max_mhz = float(out[1]); self.how = "nvidia-smi once before and once after the timed loops (no pynvml)"
+            self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+            self.how = "one nvidia-smi query while the GPU executes the enqueued timed steps (after the last launch of the resident loop)"
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
                 if "Active" in v and "Not" not in v:
-                    self.reasons.add(name)
-        except Exception:
-            pass
-
-    def sample(self):
-        """called by the timing loop between two steps"""
-        if self.nv is None:
-            return
-        try:
-            self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
-            mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            for name, bit in self.REASONS:
-                if mask & bit:
                     self.reasons.add(name)
         except Exception:
             pass
@@ -341,7 +319,6 @@ def main():
             evs.append((a, b))
         if sampler is not None:              # every step is enqueued and the GPU is still executing them: sample now, then drain
             sampler.sample()
-            sampler.sample()
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
@@ -374,7 +351,7 @@ def main():
         launches = _lib.launch_count() - launches0
         if world > 1:
             dist.barrier()
-        time.sleep(0.3)                      # NVML queries disturb CUDA submission for ~100 ms on this pool (see ClockSampler)
+        time.sleep(0.5)                      # a clock query disturbs CUDA submission for a while on this pool (see ClockSampler)
         t_e2e = timed(e2e, args.steps)
         gc.enable()
         # a separate, instrumented pass for the roofline: CUDA events around every launch of our kernels (not part of `value`)
