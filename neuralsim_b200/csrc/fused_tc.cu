@@ -339,8 +339,8 @@ template <int MODE>
 static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta &m, const __half *g, const DecoderDevTC &d, const float *x, const float *ro,
                        const float *rd, const int64_t *ridx, const float *t, int64_t n, int ml, float *sdf, const int64_t *pi, const int64_t *pr, int64_t np,
                        const OccCollect &oc) {
-    // ray-major order: libm softplus (its longer epilogue keeps fewer warps in the gather phase at once -> less L1 thrash);
-    // ray-tiled order: SFU softplus (gathers coalesce, the kernel is issue-bound again).  profiles/r01e_ab.txt
+    // default (variant 1): SFU softplus, two levels per gather trip -- fastest in both point orders (profiles/r01f_ab.txt: 4.3 ms ray-tiled,
+    // 5.0 ms ray-major on the 25.4 M boundary points of a frame; the SFU epilogue with ONE level per trip thrashes L1 in ray-major order: 13 ms).
     // variants: 0 libm / 2 levels per trip, 1 SFU / 2, 2 libm / 1, 3 SFU / 1
     if (variant < 0) variant = 1;                      // SFU softplus, two levels per trip: best in both orders (profiles/r01f_ab.txt)
     if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
