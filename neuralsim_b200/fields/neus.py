@@ -163,6 +163,12 @@ class LoTDNeuSModel(LoTDNeuS):
         ret["net_x"] = x
         return ret
 
+    @torch.no_grad()
+    def query_sdf(self, x):
+        # the base model's query: no sample collection (renderer_mixin.py:166-168 -> super().query_sdf); this is what the accel's own
+        # init / EMA update evaluate
+        return LoTDNeuS.forward_sdf(self, x)["sdf"]
+
     # ---- the accel watches every training-time SDF query (renderer_mixin.py:154-164)
     def forward_sdf(self, x, skip_accel=False, **kw):
         collect = self.accel.occ.collect_struct() if (self.training and not skip_accel and self.accel is not None) else None
