@@ -17,7 +17,7 @@ if [[ "$FLAGS" == *prof* ]]; then
   timeout 300 python profiles/torch_profile_step.py > gpurun_out/${TAG}_torch_prof.txt 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ref-cuda > gpurun_out/${TAG}_ncu_bench.log 2>&1
-  python profiles/summarize_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.md 2>&1
+  python profiles/summarize_launches.py gpurun_out/${TAG}_launches.csv 4 > gpurun_out/${TAG}_launches_summary.md 2>&1
   head -36 gpurun_out/${TAG}_launches_summary.md
 fi
 if [[ "$FLAGS" == *abs* ]]; then
