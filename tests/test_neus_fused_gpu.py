@@ -111,8 +111,8 @@ def test_composite_forward_backward(normalize_depth):
         assert rel_l2(x, y) < 1e-5
 
 
-@pytest.mark.parametrize("perturb", [False, True])
-def test_render_fused_equals_unfused_chain(perturb):
+@pytest.mark.parametrize("perturb,stages", [(False, 3), (True, 3), (False, 1), (False, 2)])
+def test_render_fused_equals_unfused_chain(perturb, stages):
     """The whole query + integration with the fused stages on and off: same samples, same image, same gradients
     (with `perturb`, from the same seed: the fused path consumes the random stream exactly as the op-by-op chain does)."""
     from neuralsim_b200.graphics import neus as G
@@ -120,6 +120,10 @@ def test_render_fused_equals_unfused_chain(perturb):
     from oracle import scene as oscene
     from util import make_pair, product_grads
     P, model = make_pair("cuda")
+    if stages != 3:                                        # fewer up-sampling stages: no merge at all (1) / one merge (2)
+        qp = dict(model.ray_query_cfg["query_param"])
+        qp.update(num_fine=[8, 8, 32][:stages] if stages == 2 else 16, upsample_inv_s_factors=[1, 4, 16][:stages])
+        model.ray_query_cfg["query_param"] = qp
     rays_o, rays_d = oscene.pinhole_rays(36, 48, oscene.orbit_camera(1, 8, radius=3.0, elev_deg=25.0))
     rays_o, rays_d = rays_o.cuda(), rays_d.cuda()
     ren = SingleVolumeRenderer(dict(near=0.01, far=None, perturb=perturb))
