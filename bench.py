@@ -337,7 +337,7 @@ def main():
         loss_host.copy_(step(o, d), non_blocking=True)                                # D2H of the step's result
         torch.cuda.current_stream().synchronize()
 
-    with ClockSampler(local, args.clock_period_ms) as clocks:          # see the class: NVML queries between the per-step event pairs
+    with ClockSampler(local, args.clock_period_ms) as clocks:          # see the class: one clock query after the last timed launch
         for i in range(args.warmup):
             resident(i)
         torch.cuda.synchronize()
