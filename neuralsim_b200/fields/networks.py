@@ -3,9 +3,10 @@
 (reference files: nr3d_lib/nr3d_lib/models/layers.py:228-312, blocks/mlp.py:26-125, fields/sdf/lotd_sdf.py:40-257,
 fields/nerf/mlp_nerf.py:188-289, embedders/spherical_harmonics/sphere_harmonics.py:14-82, fields/neus/variance.py:122-142).
 
-fp32 master weights, fp16 autocast evaluation -- the numerics contract of the reference.  The training path runs the
-layers through torch (cuBLAS GEMMs, which is what the reference does); no-grad SDF queries go through the fused
-kernel `nsb_fused_sdf*` (csrc/fused.cu) that follows the same rounding points.
+fp32 master weights, fp16 autocast evaluation -- the numerics contract of the reference.  The modules below are the
+reference's layers (torch autocast, cuBLAS) and remain the specification; the hot path replaces them by fused tcgen05
+kernels with the same rounding points: SDF queries (with or without grad) by `nsb_fused_sdf*` + `nsb_fused_sdf_bwd`
+(`_FusedSDF`, csrc/fused_tc.cu), the colour / normal query by `nsb_fused_color_*` (fields/fused_color.py, csrc/color_tc.cu).
 """
 from __future__ import annotations
 

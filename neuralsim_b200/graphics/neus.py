@@ -6,6 +6,11 @@ function `NeusRendererMixin.ray_query` dispatches to for `query_mode: march_occ_
 (renderer_mixin.py:346-350).  It returns the same packed `volume_buffer` dict (renderer_mixin.py:263-303).
 Duck-typed `model` interface: forward_sdf(x)->{'sdf'}, forward(x, v=, h_appear=, nablas_has_grad=, with_rgb=,
 with_normal=)->{'sdf','nablas','rgb','h'}, forward_inv_s(), accel.ray_march(rays_o, rays_d, near=, far=, perturb=, **march_cfg).
+
+Two implementations of the same function live here: the op-by-op chain in the reference's own formulation (every call a
+`nr3d_lib`-named wrapper of this package), and `_query_fused`, one launch per stage (csrc/neus_glue.cu, neus_fused.cu, fused_tc.cu,
+color_tc.cu), taken when the model offers `forward_sdf_on_rays` and the occupancy grid is a single 3-D grid.  FUSED_STAGES = False
+forces the chain; tests/test_neus_fused_gpu.py renders with both and compares samples, images and gradients.
 """
 from __future__ import annotations
 
