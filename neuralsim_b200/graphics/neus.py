@@ -29,7 +29,7 @@ from . import neus_fused
 # pack_ops / elementwise calls (same maths; kept for the parity tests and as documentation of what is fused).
 FUSED_STAGES = True
 import os as _os
-MARCHED_TILED = _os.environ.get("NSB_MARCHED_TILED", "1") != "0"
+MARCHED_TILED = _os.environ.get("NSB_MARCHED_TILED", "0") != "0"     # measured: 0.71 ms ray-major vs 0.99 ms ray-tiled per frame (profiles/README.md)
 
 __all__ = ["neus_cdf", "neus_ray_cdf_to_alpha", "neus_ray_sdf_to_alpha", "neus_ray_sdf_to_vw", "neus_packed_cdf_to_alpha",
            "neus_packed_sdf_to_alpha", "neus_packed_sdf_to_upsample_alpha", "neus_ray_sdf_to_upsample_alpha",
@@ -125,8 +125,9 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, perturb=False, 
     pack_infos = pinfo_march
     coherent = bool(ray_tested.get("rays_coherent", False))      # image-ordered rays: ray-tiled traversal inside the SDF kernel
     with torch.no_grad():
-        # marched packs are ragged (20-100 samples per ray): tiles of 32 rays are padded to the longest, so the ray-tiled order only pays
-        # for image-ordered rays AND when MARCHED_TILED (A/B switch; boundary and fine queries have uniform packs and are always tiled)
+        # marched packs are ragged (20-100 samples per ray): tiles of 32 rays are padded to the longest and the samples of one ray are
+        # already close together, so the ray-major order wins here (A/B switch MARCHED_TILED); the boundary and fine queries have
+        # uniform packs and are ray-tiled whenever the rays are image-ordered
         tiled_m = coherent and MARCHED_TILED
         sdf = model.forward_sdf_on_rays(ridx, depth_samples, rays_o, rays_d, packs=(pack_infos, ridx_hit) if tiled_m else None)["sdf"].to(dtype)
         fine_stages = []
