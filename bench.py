@@ -235,8 +235,12 @@ def use_reference_cuda_kernels():
     import neuralsim_b200.fields.networks as NW
     import neuralsim_b200.graphics.pack_ops as GP
     import neuralsim_b200.graphics.raymarch as GR
+    import neuralsim_b200.fields.space as SP
+    import neuralsim_b200.graphics.neus as GN
     E._backend, GP._backend, GR._backend, NW._shencoder = mods["_lotd"], mods["_pack_ops"], mods["_occ_grid"], mods["_shencoder"]
-    NW.LoTDSDF._fusable = lambda self: False
+    NW.LoTDSDF._fusable = lambda self: False       # no fused SDF / colour kernels
+    GN.FUSED_STAGES = False                        # the op-by-op chain of neus_ray_query.py / single_volume_renderer.py, every op a reference kernel or ATen
+    SP.FUSED_RAY_TEST = False                      # the torch chain of aabb.py
     return True
 
 

@@ -8,6 +8,11 @@ from ..graphics.raytest import ray_box_intersection_fast_float_nocheck
 from .. import _lib as L
 
 
+# True: ray_test of fp32 CUDA rays runs as three launches of csrc/neus_glue.cu; False: as the chain of torch ops of the reference
+# (aabb.py:71-99) -- same results (tests/test_glue_gpu.py); bench.py's reference-cuda arm switches it off.
+FUSED_RAY_TEST = True
+
+
 class AABBSpace(nn.Module):
     def __init__(self, bounding_size: float = 2.0, aabb=None, dtype=torch.float, device=None):
         super().__init__()
@@ -41,7 +46,7 @@ class AABBSpace(nn.Module):
 
     def ray_test(self, rays_o, rays_d, near=None, far=None, return_rays=True, normalized=False, **extra_ray_data):
         """Slab test against the unit cube -> dict(num_rays, rays_inds, near, far, rays_o, rays_d, **extras) of the hit rays."""
-        if (rays_o.is_cuda and rays_o.dim() == 2 and rays_o.dtype == torch.float32 and rays_d.dtype == torch.float32 and return_rays
+        if (FUSED_RAY_TEST and rays_o.is_cuda and rays_o.dim() == 2 and rays_o.dtype == torch.float32 and rays_d.dtype == torch.float32 and return_rays
                 and not rays_o.requires_grad and not rays_d.requires_grad and not isinstance(near, torch.Tensor) and not isinstance(far, torch.Tensor)):
             return self._ray_test_fused(rays_o, rays_d, near, far, normalized, extra_ray_data)
         if not normalized:
