@@ -34,9 +34,9 @@ struct SdfTile {
 };
 
 // all 128 threads: my point's table coordinates -> my sdf (fp16-rounded, as fp32).  Ends with the CTA barrier that frees tile + TMEM.
-template <bool FAST_SP, int UNROLL>
+template <bool FAST_SP, int UNROLL, bool PAIRED>
 __device__ __forceinline__ float sdf_of_tile(const SdfTile &c, const float (&xs)[3], int tid, uint32_t &phase) {
-    gather_row_to_tile<kTile, UNROLL>(c.m, c.grid, xs, c.max_level, c.sA, tid);
+    gather_row_to_tile<kTile, UNROLL, PAIRED>(c.m, c.grid, xs, c.max_level, c.sA, tid);
     tc::fence_async_smem();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ float sdf_of_tile(const SdfTile &c, const float (&xs)
     return __half2float(__float2half_rn(out + c.sb2));
 }
 
-template <int MODE, bool FAST_SP = false, int UNROLL = 2>
+template <int MODE, bool FAST_SP = false, int UNROLL = 2, bool PAIRED = false>
 __global__ void __launch_bounds__(kTile)
 k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
                const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ridx,
@@ -127,7 +127,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
                 }
 #pragma unroll
                 for (int q = 0; q < 3; ++q) xs[q] = fminf(fmaxf(__fmaf_rn(xs[q], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
-                const float v = sdf_of_tile<FAST_SP, UNROLL>(ctx, xs, tid, phase);
+                const float v = sdf_of_tile<FAST_SP, UNROLL, PAIRED>(ctx, xs, tid, phase);
                 if (valid) {
                     sdf[first + k] = v;
                     if (oc.pcl) occ_collect_point(oc, xs, v);
@@ -141,7 +141,7 @@ k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDev
             const bool valid = i < n;
             float xs[3];
             load_point(MODE == 1, x, rays_o, rays_d, ridx, t, i, valid, xs);
-            const float v = sdf_of_tile<FAST_SP, UNROLL>(ctx, xs, tid, phase);
+            const float v = sdf_of_tile<FAST_SP, UNROLL, PAIRED>(ctx, xs, tid, phase);
             if (valid) {
                 sdf[i] = v;
                 if (oc.pcl) occ_collect_point(oc, xs, v);
@@ -341,11 +341,12 @@ static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta 
                        const OccCollect &oc) {
     // default (variant 1): SFU softplus, two levels per gather trip -- fastest in both point orders (profiles/r01f_ab.txt: 4.3 ms ray-tiled,
     // 5.0 ms ray-major on the 25.4 M boundary points of a frame; the SFU epilogue with ONE level per trip thrashes L1 in ray-major order: 13 ms).
-    // variants: 0 libm / 2 levels per trip, 1 SFU / 2, 2 libm / 1, 3 SFU / 1
+    // variants: 0 libm / 2 levels per trip, 1 SFU / 2, 2 libm / 1, 3 SFU / 1, 4 SFU / 2 + paired corner loads (experiment, lotd_device.cuh)
     if (variant < 0) variant = 1;                      // SFU softplus, two levels per trip: best in both orders (profiles/r01f_ab.txt)
     if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
     else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
     else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
+    else if (variant == 4 && plmeta_pairable(m, g)) k_fused_sdf_tc<MODE, true, 2, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);   // experiment: paired corner loads
     else k_fused_sdf_tc<MODE, false, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
 }
 

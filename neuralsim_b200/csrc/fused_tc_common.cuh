@@ -37,7 +37,7 @@ constexpr int NF = 32, HW = 64;           // features, hidden width (zero padded
 // the 16 levels of one point -> row `r` of a chunk-major [R x >=32] fp16 tile (4 bytes per level)
 // U levels per loop trip: the 8 U corner loads of a trip are independent, so U = 2 doubles the loads in flight per thread (the
 // latency-bound backward kernels run at 8-16 warps / SM); full unrolling is avoided on purpose (instruction cache, see fused_tc.cu).
-template <int R, int U = 2>
+template <int R, int U = 2, bool PAIRED = false>
 __device__ __forceinline__ void gather_row_to_tile(const PLMeta &m, const __half *__restrict__ grid, const float (&xs)[3],
                                                    int max_level, uint8_t *tile, int r) {
 #pragma unroll 1
@@ -48,7 +48,9 @@ __device__ __forceinline__ void gather_row_to_tile(const PLMeta &m, const __half
 #pragma unroll
         for (int u = 0; u < U; ++u) level_cells3(m, p0 + u, xs, cell[u], w[u]);
 #pragma unroll
-        for (int u = 0; u < U; ++u) packed[u] = level_feat2_cells(level_cells_ptr(m, p0 + u, grid), cell[u], w[u]);
+        for (int u = 0; u < U; ++u)
+            packed[u] = PAIRED ? level_feat2_cells_paired(level_cells_ptr(m, p0 + u, grid), cell[u], w[u], (m.is_hash >> (p0 + u)) & 1u)
+                               : level_feat2_cells(level_cells_ptr(m, p0 + u, grid), cell[u], w[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t p = p0 + u;

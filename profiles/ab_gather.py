@@ -54,9 +54,9 @@ def run_packs(tag):
 
 
 ref = None
-for variant, name in ((2, "libm softplus, 1 level/trip"), (0, "libm softplus, 2 levels/trip"), (3, "sfu softplus, 1 level/trip"),
-                      (1, "sfu softplus, 2 levels/trip")):
-    for ctas in (7, 6, 5):
+for variant, name in ((1, "sfu softplus, 2 levels/trip (default)"), (4, "sfu, 2 levels/trip, PAIRED corner loads (experiment)"),
+                      (0, "libm softplus, 2 levels/trip")):
+    for ctas in (6, 7):
         os.environ["NSB_SDF_VARIANT"], os.environ["NSB_SDF_CTAS"] = str(variant), str(ctas)
         s = run(f"{name}, {ctas} CTA/SM")
         s2 = run_packs(f"{name}, {ctas} CTA/SM, RAY-TILED")
