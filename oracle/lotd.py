@@ -21,6 +21,8 @@ non-deterministic fp16 atomics, lotd_cuda.h:494-561, so it has no bit-exact valu
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 DENSE = 0  # lotd_types.h:16-26 (enum LoDType)
@@ -152,6 +154,33 @@ def _half_add(a16, b16):
     return (a16.astype(np.float64) + b16.astype(np.float64)).astype(np.float16)
 
 
+THREADS = [None]            # None: min(16, usable cores); set to [1] to force the serial walk
+
+
+def _usable_cpus():
+    n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+def _for_levels(fn, levels, n_points):
+    """The levels of the table are independent (disjoint output columns / gradient ranges): walk them on a thread pool (numpy releases the
+    GIL inside its vector loops) -- the CPU port should use the host cores it has, like the GPU path uses its SMs."""
+    nt = THREADS[0] or min(16, _usable_cpus())
+    if nt <= 1 or len(levels) <= 1 or n_points < 2048:
+        for l in levels:
+            fn(l)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(nt, len(levels))) as ex:
+        list(ex.map(fn, levels))
+
+
 def _level_iter(meta, max_level):
     F = meta.n_feat_per_pseudo_lvl
     for psl in range(meta.n_pseudo_levels):
@@ -177,7 +206,9 @@ def lod_fwd(meta: LoDMeta, x, params, max_level=None, need_input_grad=False):
     if max_level <= -1:
         return y, dy_dx
     F = meta.n_feat_per_pseudo_lvl
-    for psl, lvl, loff, foff, ooff in _level_iter(meta, max_level):
+
+    def one_level(args):
+        psl, lvl, loff, foff, ooff = args
         res = np.array(meta.level_res_multidim[lvl], dtype=np.uint32)
         scale = (res - 2).astype(np.float32)
         nf = meta.level_n_feats[lvl]
@@ -210,6 +241,8 @@ def lod_fwd(meta: LoDMeta, x, params, max_level=None, need_input_grad=False):
                     # grads += w*diff is an FFMA on device: product exact in fp64, one rounding
                     g = (g.astype(np.float64) + w[:, None].astype(np.float64) * diff.astype(np.float64)).astype(np.float32)
                 dy_dx[:, ooff:ooff + F, gd] = g
+
+    _for_levels(one_level, list(_level_iter(meta, max_level)), N)
     return y, dy_dx
 
 
@@ -229,7 +262,8 @@ def lod_bwd_grid(meta: LoDMeta, dL_dy, x, n_params, max_level=None):
         return grad
     F = meta.n_feat_per_pseudo_lvl
     g32 = dL_dy.astype(np.float32)
-    for psl, lvl, loff, foff, ooff in _level_iter(meta, max_level):
+    def one_level(args):                     # every (pseudo) level writes its own range of `grad`
+        psl, lvl, loff, foff, ooff = args
         res = np.array(meta.level_res_multidim[lvl], dtype=np.uint32)
         scale = (res - 2).astype(np.float32)
         nf = meta.level_n_feats[lvl]
@@ -238,6 +272,10 @@ def lod_bwd_grid(meta: LoDMeta, dL_dy, x, n_params, max_level=None):
             gi = grid_index(meta, lvl, cell + off) * nf + foff + loff
             for f in range(F):
                 np.add.at(grad, gi + f, g32[:, ooff + f].astype(np.float64) * w.astype(np.float64))
+
+    levels = list(_level_iter(meta, max_level))
+    # pseudo levels of one level share its range (map_cnt): keep those on one thread; the shipped configurations have one pseudo level per level
+    _for_levels(one_level, levels, N) if len({l[1] for l in levels}) == len(levels) else [one_level(l) for l in levels]
     return grad
 
 

@@ -132,3 +132,25 @@ def test_cfg1_sphere_pure_torch_cpu():
     hit = out["mask_volume"] > 0.5
     assert 0.02 < float(hit.float().mean()) < 0.5                 # the r=0.5 sphere seen from 4 units away
     assert abs(float(out["depth_volume"][hit].min()) - 3.5) < 0.1
+
+
+def test_threaded_level_walk_equals_serial():
+    """oracle/lotd.py walks the independent levels on a thread pool for large inputs: same bits as the serial walk."""
+    from oracle import lotd as olotd
+    cfg = dict(lod_res=[8, 12, 18, 24, 40, 64, 100, 160], lod_n_feats=[2] * 8, lod_types=["Dense"] * 4 + ["Hash"] * 4, hashmap_size=2 ** 14)
+    meta = olotd.LoDMeta(3, **cfg)
+    rng = np.random.default_rng(5)
+    p = rng.uniform(-0.1, 0.1, meta.n_params).astype(np.float16)
+    x = rng.uniform(1e-6, 1 - 1e-6, (6000, 3)).astype(np.float32)
+    g = rng.standard_normal((6000, meta.n_encoded_dims)).astype(np.float32)
+    out = {}
+    for nt in (1, 8):
+        olotd.THREADS[0] = nt
+        try:
+            y, d = olotd.lod_fwd(meta, x, p, None, True)
+            gr = olotd.lod_bwd_grid(meta, g, x, meta.n_params)
+        finally:
+            olotd.THREADS[0] = None
+        out[nt] = (y, d, gr)
+    for a, b in zip(out[1], out[8]):
+        assert np.array_equal(a, b)
