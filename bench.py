@@ -23,7 +23,6 @@ import math
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np

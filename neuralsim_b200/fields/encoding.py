@@ -6,8 +6,7 @@ LoTDFunction / LoTDFunctionFwdDydx / LoTDFunctionBwdDydx; the kernels behind the
 """
 from __future__ import annotations
 
-from math import prod
-from typing import List, Optional, Union
+from typing import Optional
 
 import numpy as np
 import torch

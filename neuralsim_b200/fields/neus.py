@@ -8,7 +8,6 @@ State-dict names follow the reference so checkpoints keep loading (SURVEY.md §9
 from __future__ import annotations
 
 import ctypes
-from types import SimpleNamespace
 
 import torch
 import torch.nn as nn

@@ -17,7 +17,6 @@ from __future__ import annotations
 from operator import itemgetter
 
 import torch
-import torch.nn.functional as F
 
 from .nerf import packed_alpha_to_vw, packed_volume_render_compression, ray_alpha_to_vw
 from .pack_ops import (get_pack_infos_from_batch, merge_two_batch_a_includes_b, merge_two_packs_sorted_aligned,
