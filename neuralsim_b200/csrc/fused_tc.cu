@@ -21,54 +21,6 @@ namespace nsb {
 //         cells -> few 128 B lines per request; the L1 tag stage (one line per ~2 cycles) is what bounds this kernel
 //         (profiles/r01d_ab.txt: 12.6 -> 7.4 ms on the boundary points of a frame).  sdf is written to the packed slot, so
 //         nothing downstream changes.  Incoherent rays (random training pixels) keep MODE 1: locality along the ray.
-struct SdfTile {
-    const PLMeta &m;
-    const __half *grid;
-    int max_level;
-    uint8_t *sA;
-    uint32_t a_addr, b_addr, idesc, tmem, lane_base;
-    uint64_t *mbar;
-    const float *sb1, *sW2;
-    float sb2;
-    SoftplusK spk;
-};
-
-// all 128 threads: my point's table coordinates -> my sdf (fp16-rounded, as fp32).  Ends with the CTA barrier that frees tile + TMEM.
-template <bool FAST_SP, int UNROLL, bool PAIRED>
-__device__ __forceinline__ float sdf_of_tile(const SdfTile &c, const float (&xs)[3], int tid, uint32_t &phase) {
-    gather_row_to_tile<kTile, UNROLL, PAIRED>(c.m, c.grid, xs, c.max_level, c.sA, tid);
-    tc::fence_async_smem();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (tid == 0) {
-        tc::fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < NF / 16; ++ks)
-            tc::mma_f16_ss(c.tmem, tc::make_desc(c.a_addr + ks * 2 * (kTile * 16), kTile * 16, 128),
-                           tc::make_desc(c.b_addr + ks * 2 * (HW * 16), HW * 16, 128), c.idesc, ks > 0);
-        tc::commit(c.mbar);
-    }
-    tc::mbar_wait(c.mbar, phase);
-    phase ^= 1;
-    tc::fence_after_sync();
-    float out = 0.f;
-#pragma unroll 1
-    for (int ch = 0; ch < HW / 8; ++ch) {
-        float z[8];
-        tc::tmem_ld8(c.tmem + c.lane_base + ch * 8, z);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float zz = __half2float(__float2half_rn(z[j] + c.sb1[ch * 8 + j]));
-            float sp;
-            if (FAST_SP) sp = softplus_a(zz, c.spk);
-            else { const float zb = zz * c.spk.beta; sp = zb > 20.f ? zz : log1pf(expf(zb)) * (1.f / c.spk.beta); }
-            out = fmaf(__half2float(__float2half_rn(sp)), c.sW2[ch * 8 + j], out);
-        }
-    }
-    tc::fence_before_sync();               // TMEM reads done before the next tile's MMA overwrites Z
-    __syncthreads();
-    return __half2float(__float2half_rn(out + c.sb2));
-}
-
 template <int MODE, bool FAST_SP = false, int UNROLL = 2, bool PAIRED = false>
 __global__ void __launch_bounds__(kTile)
 k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
