@@ -321,3 +321,32 @@ def composite(alpha, t, pack_infos, rgb=None, nablas=None, normalize_depth=True,
     vw, mask, depth, rgb_o, nab_o = _Composite.apply(alpha, t, rgb, nablas, pack_infos, normalize_depth, early_stop_eps, alpha_thre,
                                                      ray_index, n_rays)
     return vw, mask, depth, (rgb_o if rgb is not None else None), (nab_o if nablas is not None else None)
+
+
+@torch.no_grad()
+def upsample_persistent(surface, ridx_hit, pack_infos, t_starts, rays_o, rays_d, inv_s_stages, num_fine, use_estimate_alpha=False,
+                        early_stop_eps=1e-4, alpha_thre=0.0, max_level=None):
+    """EXPERIMENT (csrc/ray_upsample.cu, not on the default path): all up-sampling stages of the hit rays in one persistent kernel.
+    surface: LoTDSDF (fused query state); inv_s_stages[i] = upsample_inv_s * factor_i; num_fine: odd-ised sample counts per stage.
+    -> (fine_all [n_hit, sum(num_fine)], overflow int32 [n_hit]: 1 = this ray did not fit, its row is undefined)."""
+    grid16, dec = surface._fused_state()
+    n_hit, dev = ridx_hit.shape[0], t_starts.device
+    n_stage = len(num_fine)
+    us = []
+    for n in num_fine:
+        key = (n, dev)
+        u = _U_CACHE.get(key)
+        if u is None:
+            u = _U_CACHE[key] = torch.linspace(0., 1., n + 2, device=dev, dtype=torch.float32)[1:-1].contiguous()
+        us.append(u)
+    fine_all = torch.empty(n_hit, int(sum(num_fine)), dtype=torch.float32, device=dev)
+    overflow = torch.zeros(n_hit, dtype=torch.int32, device=dev)
+    nf = (ctypes.c_int32 * n_stage)(*[int(n) for n in num_fine])
+    invs = (ctypes.c_float * n_stage)(*[float(v) for v in inv_s_stages])
+    up = (ctypes.c_void_p * n_stage)(*[u.data_ptr() for u in us])
+    L.check(L.lib().nsb_upsample_persistent(surface.encoding.meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"),
+                                            L.ptr(t_starts, "f32"), L.ptr(pack_infos, "i64"), L.ptr(ridx_hit, "i64"), L.c_i64(n_hit),
+                                            L.c_i32(surface._ml(max_level)), L.c_i32(n_stage), nf, invs, up, L.c_i32(1 if use_estimate_alpha else 0),
+                                            L.c_f32(early_stop_eps), L.c_f32(alpha_thre), L.ptr(fine_all), L.ptr(overflow), L.stream_ptr()),
+            "upsample_persistent")
+    return fine_all, overflow
