@@ -217,6 +217,39 @@ int nsb_fused_sdf_bwd(const nsb_lotd_meta *meta_host, const void *params_half, c
                       const float *d_sdf, int64_t n, int32_t max_level, float *d_grid, float *d_W1, float *d_b1,
                       float *d_W2, float *d_b2, void *stream);
 
+/* the same with an index list: row i of the launch is sample keep[i] of (ridx, t, d_sdf) / (x, d_sdf) -- the compaction of the samples
+ * with a non-zero cotangent (most boundary samples of a NeuS ray carry none) without a gather of the operands.  keep == NULL: identity. */
+int nsb_fused_sdf_bwd_indexed(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host,
+                              const float *x, const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t,
+                              const float *d_sdf, const int64_t *keep, int64_t n, int32_t max_level, float *d_grid, float *d_W1,
+                              float *d_b1, float *d_W2, float *d_b2, void *stream);
+
+/* ---------------------------------------------------------------- device-resident sizes (a step without host reads)
+ * The reference reads every data-dependent size back to the host (`.item()`, `nonzero()`: ~25 syncs per ray_query).
+ * Here a size may stay in device memory: nsb_bind_device_counts(c0, c1) binds one or two device int64 to the calling thread; the NEXT
+ * count-aware entry point of that thread consumes (and clears) the binding and its kernel processes min(n_arg, *c0) items -- n_arg
+ * (the `n` / `n_packs` / `n_rays` / `n_list` argument) then is the CAPACITY the buffers and the grid were sized for.  c1 is the second
+ * count of nsb_assemble_boundary (n_hit).  Count-aware: nsb_gather_rays, nsb_ray_marching_listed (first round: num_steps of the rays
+ * in [*c0, n_rays) is written as 0; second round: the listed rays), nsb_fused_sdf_collect / _rays / _packs, nsb_fused_sdf_bwd(_indexed),
+ * nsb_neus_upsample_cdf, nsb_packed_invert_cdf_shared_u, nsb_merge_sorted_vals, nsb_assemble_boundary, nsb_neus_alpha_forward
+ * (num_steps of the packs in [*c0, n_packs) is written as 0) / _backward, nsb_compact_samples, nsb_scatter_f32, nsb_flag_nonzero,
+ * nsb_fused_color_fwd / _bwd, nsb_composite_forward / _backward.  With every size on the device a whole fwd+bwd step has no host
+ * read and can be captured in a CUDA graph (neuralsim_b200/graphics/neus_static.py). */
+int nsb_bind_device_counts(const int64_t *count0, const int64_t *count1);
+/* flag[i] = (v[i] != 0) for i < live count, 0 up to n (count-aware). */
+int nsb_flag_nonzero(const float *v, int64_t n, int32_t *flag, void *stream);
+/* Derived sizes of one NeuS query in a device block `counts` of >= 32 int64 (zero-filled once per query):
+ *   written by nsb_scan_counts (totals = counts + 0 / + 3 / + 6 / + 9):
+ *     [0] rays that pass the box test  [2] coherent neighbour pairs   [3] M marched samples  [4] n_hit rays with samples
+ *     [6] K samples kept by the compression  [7] rays that keep samples   [9] samples with a non-zero cotangent (backward)
+ *   written here, phase 0 (after the march scan):  [12] M and [13] n_hit (both 0 if the arena `march_cap` cannot hold the merged
+ *     samples -- then bit 0 of [20] is set), [14+q] n_hit * n_fine[q], [22+q] samples in the merged buffer after stage q,
+ *     [18] S = n_rays n_coarse + n_hit sum(n_fine)
+ *   phase 1 (after the scan of the kept counts): [19] K and [21] rays that keep samples (0 and bit 1 of [20] if K > kept_cap),
+ *     [26] = [0] if K fits, else 0 (the count nsb_compact_samples is bound to). */
+int nsb_query_counts(int64_t *counts, int32_t phase, int32_t n_coarse, const int32_t *n_fine_host, int32_t n_stage, int64_t march_cap,
+                     int64_t kept_cap, void *stream);
+
 /* ---------------------------------------------------------------- fused per-ray NeuS stages (csrc/neus_fused.cu)
  * One warp per ray (pack).  Each entry point replaces a chain of the reference's Python-level calls with one launch;
  * the pack_ops entry points above remain the drop-in for `_pack_ops` itself.

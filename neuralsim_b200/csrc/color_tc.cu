@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kTile)
 k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev net, const PointSrc ps, const float *__restrict__ view_dirs,
             const float *__restrict__ h_appear, int64_t n, int max_level, float *__restrict__ sdf_out, float *__restrict__ nab_out,
             float *__restrict__ rgb_out, float *__restrict__ x_out, uint8_t *__restrict__ Zt, uint8_t *__restrict__ Xt,
-            uint8_t *__restrict__ Y1t, uint8_t *__restrict__ Y2t, const OccCollect oc) {
+            uint8_t *__restrict__ Y1t, uint8_t *__restrict__ Y2t, const OccCollect oc, const int64_t *__restrict__ n_dev) {
+    n = eff_n(n, n_dev);
     extern __shared__ uint8_t dyn_smem[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
     uint8_t *sX = tiles;                                       // 16 KB [h | x sh n ha 0]
@@ -369,7 +370,8 @@ __global__ void __launch_bounds__(kTile)
 k_color_rad_bwd(const ColorNetDev net, const uint8_t *__restrict__ Xt, const uint8_t *__restrict__ Y1t, const uint8_t *__restrict__ Y2t,
                 const float *__restrict__ rgb, const float *__restrict__ g_rgb, int64_t n, float *__restrict__ dh_out,
                 float *__restrict__ dR1, float *__restrict__ drb1, float *__restrict__ dR2, float *__restrict__ drb2,
-                float *__restrict__ dR3, float *__restrict__ drb3) {
+                float *__restrict__ dR3, float *__restrict__ drb3, const int64_t *__restrict__ n_dev) {
+    n = eff_n(n, n_dev);
     constexpr int NE = 80;                                     // 64 columns + the [1, gy3, 0..] chunk + a zero chunk (N % 16 == 0)
     extern __shared__ uint8_t dyn_smem[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
@@ -561,7 +563,8 @@ __global__ void __launch_bounds__(kTile)
 k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev net, const PointSrc ps, const uint8_t *__restrict__ Zt,
                 const uint8_t *__restrict__ Xt, const float *__restrict__ g_nab, const float *__restrict__ g_sdf, const float *__restrict__ dh_r,
                 int64_t n, int max_level, float *__restrict__ d_grid, float *__restrict__ d_W1, float *__restrict__ d_b1, float *__restrict__ d_W2,
-                float *__restrict__ d_b2) {
+                float *__restrict__ d_b2, const int64_t *__restrict__ n_dev) {
+    n = eff_n(n, n_dev);
     constexpr int NX = 48;                                     // 32 + the [1 0..] chunk + a zero chunk (N % 16 == 0)
     extern __shared__ uint8_t dyn_smem[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
@@ -809,6 +812,7 @@ extern "C" int nsb_fused_color_fwd(const nsb_lotd_meta *meta, const void *params
                                    const float *rays_d, const int64_t *ridx, const float *t, const float *view_dirs, const float *h_appear,
                                    int64_t n, int32_t max_level, float *sdf, float *nablas, float *rgb, float *x_out, void *act_z, void *act_x,
                                    void *act_y1, void *act_y2, const nsb_occ_collect *collect, void *stream) {
+    const DevCounts dn = take_counts();
     if (n == 0) return 0;
     NSB_REQUIRE(meta && params_half && net && sdf && nablas && rgb && view_dirs, "nsb_fused_color_fwd: NULL argument");
     NSB_REQUIRE(x || (rays_o && rays_d && t), "nsb_fused_color_fwd: need x or (rays_o, rays_d, t)");
@@ -818,13 +822,13 @@ extern "C" int nsb_fused_color_fwd(const nsb_lotd_meta *meta, const void *params
     if (int rc = make_net(net, meta, &m, &d, "nsb_fused_color_fwd")) return rc;
     NSB_REQUIRE(d.n_appear == 0 || h_appear, "nsb_fused_color_fwd: h_appear is NULL but the net has %d appearance channels", d.n_appear);
     constexpr int kSmem = 2 * kTileBytes + 2 * HW * NF * 2 + 2 * XW * XW * 2 + 1024;
-    cudaFuncSetAttribute(k_color_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    opt_in_smem(k_color_fwd, kSmem);
     PointSrc ps{x, rays_o, rays_d, t, ridx};
     OccCollect oc{nullptr, 1, 1, 1, 0.f};
     if (collect && collect->grid_pcl) oc = OccCollect{collect->grid_pcl, collect->res[0], collect->res[1], collect->res[2], collect->inv_s};
     k_color_fwd<<<tiles_grid(n, 3), kTile, kSmem, (cudaStream_t)stream>>>(m, (const __half *)params_half, d, ps, view_dirs, h_appear, n,
                                                                           max_level < 0 ? -1 : max_level, sdf, nablas, rgb, x_out, (uint8_t *)act_z,
-                                                                          (uint8_t *)act_x, (uint8_t *)act_y1, (uint8_t *)act_y2, oc);
+                                                                          (uint8_t *)act_x, (uint8_t *)act_y1, (uint8_t *)act_y2, oc, dn.a);
     return check_launch("nsb_fused_color_fwd");
 }
 
@@ -834,6 +838,7 @@ extern "C" int nsb_fused_color_bwd(const nsb_lotd_meta *meta, const void *params
                                    const float *g_nablas, const float *g_rgb, float *dh_scratch, float *d_grid, float *d_W1, float *d_b1,
                                    float *d_W2, float *d_b2, float *d_R1, float *d_rb1, float *d_R2, float *d_rb2, float *d_R3, float *d_rb3,
                                    void *stream) {
+    const DevCounts dn = take_counts();
     if (n == 0) return 0;
     NSB_REQUIRE(meta && params_half && net && act_z && act_x && act_y1 && act_y2 && rgb && dh_scratch, "nsb_fused_color_bwd: NULL argument");
     NSB_REQUIRE(d_grid && d_W1 && d_b1 && d_W2 && d_b2 && d_R1 && d_rb1 && d_R2 && d_rb2 && d_R3 && d_rb3, "nsb_fused_color_bwd: NULL gradient buffer");
@@ -845,16 +850,16 @@ extern "C" int nsb_fused_color_bwd(const nsb_lotd_meta *meta, const void *params
     const float *dh = nullptr;
     if (g_rgb) {
         constexpr int kSmemR = 3 * kTileBytes + 2 * kTile * 80 * 2 + XW * XW * 2 + NF * XW * 2 + 1024;
-        cudaFuncSetAttribute(k_color_rad_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemR);
+        opt_in_smem(k_color_rad_bwd, kSmemR);
         k_color_rad_bwd<<<tiles_grid(n, 2), kTile, kSmemR, s>>>(d, (const uint8_t *)act_x, (const uint8_t *)act_y1, (const uint8_t *)act_y2, rgb, g_rgb, n,
-                                                                dh_scratch, d_R1, d_rb1, d_R2, d_rb2, d_R3, d_rb3);
+                                                                dh_scratch, d_R1, d_rb1, d_R2, d_rb2, d_R3, d_rb3, dn.a);
         if (int rc = check_launch("nsb_fused_color_bwd(radiance)")) return rc;
         dh = dh_scratch;
     }
     constexpr int kSmemS = 3 * kTileBytes + 2 * kTile * 48 * 2 + 2 * HW * NF * 2 + 1024;
-    cudaFuncSetAttribute(k_color_sdf_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemS);
+    opt_in_smem(k_color_sdf_bwd, kSmemS);
     PointSrc ps{x, rays_o, rays_d, t, ridx};
     k_color_sdf_bwd<<<tiles_grid(n, 2), kTile, kSmemS, s>>>(m, (const __half *)params_half, d, ps, (const uint8_t *)act_z, (const uint8_t *)act_x, g_nablas,
-                                                            g_sdf, dh, n, max_level < 0 ? -1 : max_level, d_grid, d_W1, d_b1, d_W2, d_b2);
+                                                            g_sdf, dh, n, max_level < 0 ? -1 : max_level, d_grid, d_W1, d_b1, d_W2, d_b2, dn.a);
     return check_launch("nsb_fused_color_bwd(sdf)");
 }

@@ -17,6 +17,21 @@ void set_error(const char *fmt, ...) {
 
 namespace nsb { std::atomic<int> g_opt_sdf_simt{0}; }
 
+namespace nsb {
+static thread_local DevCounts g_counts{nullptr, nullptr};
+DevCounts take_counts() {
+    const DevCounts c = g_counts;
+    g_counts = DevCounts{nullptr, nullptr};
+    return c;
+}
+}  // namespace nsb
+
+// See include/neuralsim_b200.h: the binding is consumed (and cleared) by the next count-aware launch of this thread.
+extern "C" int nsb_bind_device_counts(const int64_t *count0, const int64_t *count1) {
+    nsb::g_counts = nsb::DevCounts{count0, count1};
+    return 0;
+}
+
 // Tunables / self-check switches.  "sdf_simt" = 1 routes nsb_fused_sdf* through the CUDA-core reference kernel of
 // csrc/fused.cu instead of the tcgen05 kernel (used by the tests to cross-check the two).
 extern "C" int nsb_set_option(const char *key, int value) {

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(kTile)
 k_fused_sdf_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
                const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ridx,
                const float *__restrict__ t, int64_t n, int max_level, float *__restrict__ sdf, const int64_t *__restrict__ pack_infos,
-               const int64_t *__restrict__ pack_ray, int64_t n_packs, const OccCollect oc) {
+               const int64_t *__restrict__ pack_ray, int64_t n_packs, const OccCollect oc, const int64_t *__restrict__ n_dev) {
+    if (MODE == 2) n_packs = eff_n(n_packs, n_dev); else n = eff_n(n, n_dev);       // device-resident count (nsb_bind_device_counts)
     __shared__ __align__(1024) uint8_t sA[kTile * NF * 2];   // 8 KB : features, chunk-major core-matrix layout
     __shared__ __align__(1024) uint8_t sB[HW * NF * 2];      // 4 KB : W1 [64 x 32], same layout
     __shared__ float sb1[HW], sW2[HW];
@@ -120,7 +121,9 @@ __global__ void __launch_bounds__(kTile)
 k_sdf_bwd_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ x,
              const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ridx,
              const float *__restrict__ t, const float *__restrict__ d_sdf, int64_t n, int max_level, float *__restrict__ d_grid,
-             float *__restrict__ d_W1, float *__restrict__ d_b1, float *__restrict__ d_W2, float *__restrict__ d_b2) {
+             float *__restrict__ d_W1, float *__restrict__ d_b1, float *__restrict__ d_W2, float *__restrict__ d_b2,
+             const int64_t *__restrict__ keep, const int64_t *__restrict__ n_dev) {
+    n = eff_n(n, n_dev);
     constexpr int NX = 40, GW = 128;                          // NX: features + [1,0,..] chunk; GW: dz | d*a
     extern __shared__ uint8_t dyn_smem[];                     // 50 KB of tiles (> the 48 KB static limit), 1 KB aligned by hand
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
@@ -167,8 +170,9 @@ k_sdf_bwd_tc(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC
 
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kTile + tid;
-        const bool valid = i < n;
+        const int64_t i_ = tile * kTile + tid;
+        const bool valid = i_ < n;
+        const int64_t i = (valid && keep) ? keep[i_] : i_;        // optional index list: the samples with a non-zero cotangent
         float xs[3];
         load_point(FROM_RAYS, x, rays_o, rays_d, ridx, t, i, valid, xs);
         const float dd = valid ? d_sdf[i] : 0.f;
@@ -290,16 +294,16 @@ static inline unsigned persistent_grid(int64_t n, int ctas_per_sm) {
 template <int MODE>
 static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta &m, const __half *g, const DecoderDevTC &d, const float *x, const float *ro,
                        const float *rd, const int64_t *ridx, const float *t, int64_t n, int ml, float *sdf, const int64_t *pi, const int64_t *pr, int64_t np,
-                       const OccCollect &oc) {
+                       const OccCollect &oc, const int64_t *nd) {
     // default (variant 1): SFU softplus, two levels per gather trip -- fastest in both point orders (profiles/r01f_ab.txt: 4.3 ms ray-tiled,
     // 5.0 ms ray-major on the 25.4 M boundary points of a frame; the SFU epilogue with ONE level per trip thrashes L1 in ray-major order: 13 ms).
     // variants: 0 libm / 2 levels per trip, 1 SFU / 2, 2 libm / 1, 3 SFU / 1, 4 SFU / 2 + paired corner loads (experiment, lotd_device.cuh)
     if (variant < 0) variant = 1;                      // SFU softplus, two levels per trip: best in both orders (profiles/r01f_ab.txt)
-    if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
-    else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
-    else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
-    else if (variant == 4 && plmeta_pairable(m, g)) k_fused_sdf_tc<MODE, true, 2, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);   // experiment: paired corner loads
-    else k_fused_sdf_tc<MODE, false, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc);
+    if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
+    else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
+    else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
+    else if (variant == 4 && plmeta_pairable(m, g)) k_fused_sdf_tc<MODE, true, 2, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);   // experiment: paired corner loads
+    else k_fused_sdf_tc<MODE, false, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
 }
 
 // mode 0: x[n,3];  1: (rays_o, rays_d, ridx, t)[n];  2: ray-tiled packs (pack_infos[n_packs,2], pack_ray[n_packs] or NULL, t, sdf packed)
@@ -307,6 +311,7 @@ extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *pa
                                        const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, int64_t n,
                                        int32_t max_level, float *sdf, void *stream, int mode, const int64_t *pack_infos,
                                        const int64_t *pack_ray, int64_t n_packs, const nsb_occ_collect *collect) {
+    const DevCounts dn = take_counts();
     PLMeta m;
     if (make_plmeta(meta, &m)) return 2;
     NSB_REQUIRE(m.n_pseudo == 16 && m.F == 2 && m.D == 3 && plmeta_two_feature_cells(m), "nsb_fused_sdf (tensor-core): built for 16 x 2 LoTD features in 3-D");
@@ -314,8 +319,10 @@ extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *pa
     DecoderDevTC d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2, dec->width,
                    dec->beta};
     // NSB_SDF_VARIANT / NSB_SDF_CTAS: profiling switches (profiles/ab_gather.py); see launch_sdf
-    const int variant = getenv("NSB_SDF_VARIANT") ? atoi(getenv("NSB_SDF_VARIANT")) : -1;
-    const int ctas = getenv("NSB_SDF_CTAS") ? atoi(getenv("NSB_SDF_CTAS")) : 6;      // <= 8 (TMEM: 8 x 64 columns); 6 measured best
+    // read per call on purpose: profiles/ab_gather.py flips them between launches (two getenv of short names, ~50 ns)
+    const char *ev = getenv("NSB_SDF_VARIANT"), *ec = getenv("NSB_SDF_CTAS");
+    const int variant = ev ? atoi(ev) : -1;
+    const int ctas = ec ? atoi(ec) : 6;      // <= 8 (TMEM: 8 x 64 columns); 6 measured best
     cudaStream_t s = (cudaStream_t)stream;
     const int ml = max_level < 0 ? -1 : max_level;
     const __half *g = (const __half *)params_half;
@@ -323,9 +330,9 @@ extern "C" int nsb_fused_sdf_tc_launch(const nsb_lotd_meta *meta, const void *pa
     if (collect && collect->grid_pcl) oc = OccCollect{collect->grid_pcl, collect->res[0], collect->res[1], collect->res[2], collect->inv_s};
     if (mode == 2) {
         const int64_t groups = (n_packs + 31) / 32, wave = (int64_t)sm_count() * ctas;
-        launch_sdf<2>(variant, (unsigned)(groups < wave ? groups : wave), s, m, g, d, nullptr, rays_o, rays_d, nullptr, t, n, ml, sdf, pack_infos, pack_ray, n_packs, oc);
-    } else if (mode == 1) launch_sdf<1>(variant, persistent_grid(n, ctas), s, m, g, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf, nullptr, nullptr, 0, oc);
-    else launch_sdf<0>(variant, persistent_grid(n, ctas), s, m, g, d, x, nullptr, nullptr, nullptr, nullptr, n, ml, sdf, nullptr, nullptr, 0, oc);
+        launch_sdf<2>(variant, (unsigned)(groups < wave ? groups : wave), s, m, g, d, nullptr, rays_o, rays_d, nullptr, t, n, ml, sdf, pack_infos, pack_ray, n_packs, oc, dn.a);
+    } else if (mode == 1) launch_sdf<1>(variant, persistent_grid(n, ctas), s, m, g, d, nullptr, rays_o, rays_d, ridx, t, n, ml, sdf, nullptr, nullptr, 0, oc, dn.a);
+    else launch_sdf<0>(variant, persistent_grid(n, ctas), s, m, g, d, x, nullptr, nullptr, nullptr, nullptr, n, ml, sdf, nullptr, nullptr, 0, oc, dn.a);
     return check_launch("nsb_fused_sdf(tc)");
 }
 
@@ -333,6 +340,15 @@ extern "C" int nsb_fused_sdf_bwd(const nsb_lotd_meta *meta, const void *params_h
                                  const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, const float *d_sdf,
                                  int64_t n, int32_t max_level, float *d_grid, float *d_W1, float *d_b1, float *d_W2, float *d_b2,
                                  void *stream) {
+    return nsb_fused_sdf_bwd_indexed(meta, params_half, dec, x, rays_o, rays_d, ridx, t, d_sdf, nullptr, n, max_level, d_grid, d_W1, d_b1, d_W2, d_b2,
+                                     stream);
+}
+
+extern "C" int nsb_fused_sdf_bwd_indexed(const nsb_lotd_meta *meta, const void *params_half, const nsb_sdf_decoder *dec, const float *x,
+                                         const float *rays_o, const float *rays_d, const int64_t *ridx, const float *t, const float *d_sdf,
+                                         const int64_t *keep, int64_t n, int32_t max_level, float *d_grid, float *d_W1, float *d_b1, float *d_W2,
+                                         float *d_b2, void *stream) {
+    const DevCounts dn = take_counts();
     if (n == 0) return 0;
     NSB_REQUIRE(meta && params_half && dec && d_sdf && d_grid && d_W1 && d_b1 && d_W2 && d_b2, "nsb_fused_sdf_bwd: NULL argument");
     NSB_REQUIRE(x || (rays_o && rays_d && t), "nsb_fused_sdf_bwd: need x or (rays_o, rays_d, t)");
@@ -343,14 +359,14 @@ extern "C" int nsb_fused_sdf_bwd(const nsb_lotd_meta *meta, const void *params_h
     DecoderDevTC d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2, dec->width,
                    dec->beta};
     constexpr int kBwdSmem = (128 * 40 + 128 * 128 + 64 * 32 + 32 * 64) * 2 + 1024;
-    cudaFuncSetAttribute(k_sdf_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-    cudaFuncSetAttribute(k_sdf_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    opt_in_smem(k_sdf_bwd_tc<true>, kBwdSmem);
+    opt_in_smem(k_sdf_bwd_tc<false>, kBwdSmem);
     const unsigned grid = persistent_grid(n, 4);           // TMEM: 4 x 128 columns per SM; smem 4 x 51 KB
     cudaStream_t s = (cudaStream_t)stream;
     const int ml = max_level < 0 ? -1 : max_level;
     if (x == nullptr) k_sdf_bwd_tc<true><<<grid, kTile, kBwdSmem, s>>>(m, (const __half *)params_half, d, nullptr, rays_o, rays_d, ridx, t, d_sdf, n, ml,
-                                                                d_grid, d_W1, d_b1, d_W2, d_b2);
+                                                                d_grid, d_W1, d_b1, d_W2, d_b2, keep, dn.a);
     else k_sdf_bwd_tc<false><<<grid, kTile, kBwdSmem, s>>>(m, (const __half *)params_half, d, x, nullptr, nullptr, nullptr, nullptr, d_sdf, n, ml,
-                                                    d_grid, d_W1, d_b1, d_W2, d_b2);
+                                                    d_grid, d_W1, d_b1, d_W2, d_b2, keep, dn.a);
     return check_launch("nsb_fused_sdf_bwd");
 }

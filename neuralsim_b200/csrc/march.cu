@@ -27,6 +27,8 @@ struct MarchArgs {
     const int64_t *ray_list;       // second round only: the rays to re-march (those with samples); NULL = all n_rays
     int64_t n_list;
     const uint32_t *grid_bits;     // optional: the grid already packed 32 cells / word (nsb_pack_occ_bits), copied instead of re-packed per CTA
+    const int64_t *n_dev;          // optional device-resident count (nsb_bind_device_counts): of the rays (first round: num_steps of the rays
+                                   // between it and n_rays is written as 0) or of the listed rays (second round)
 };
 
 __device__ __forceinline__ float calc_dt(float t, float dt_gamma, float dt_min, float dt_max) {
@@ -67,7 +69,12 @@ __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
     const bool first_round = (a.packed_info == nullptr);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_work = a.ray_list ? a.n_list : a.n_rays;
+    const int64_t n_live = eff_n(n_work, a.n_dev);
     for (int64_t j_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j_ < n_work; j_ += stride) {
+        if (j_ >= n_live) {
+            if (first_round && !a.ray_list) { a.num_steps[j_] = 0; continue; }
+            break;
+        }
         const int64_t i = a.ray_list ? a.ray_list[j_] : j_;
         int b = 0;
         if (a.batch_inds) {
@@ -181,24 +188,21 @@ extern "C" int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, cons
                                        const int32_t *packed_info, int32_t *num_steps, float *t_starts, float *t_ends, int32_t *ridx,
                                        int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, const uint32_t *grid_bits,
                                        void *stream) {
+    const DevCounts dn = take_counts();
     if (n_rays == 0 || (ray_list && n_list == 0)) return 0;
     NSB_REQUIRE(rays_o && rays_d && t_min && t_max && roi && grid_binary, "nsb_ray_marching: NULL input");
     NSB_REQUIRE(rx > 0 && ry > 0 && rz > 0, "nsb_ray_marching: bad grid resolution");
     if (packed_info == nullptr) NSB_REQUIRE(num_steps && !ray_list, "nsb_ray_marching: first round needs num_steps (and marches every ray)");
     else NSB_REQUIRE(t_starts && ridx, "nsb_ray_marching: second round needs t_starts and ridx (t_ends / gidx / bidx are optional)");
     MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, batch_inds, rx, ry, rz, grid_binary, step_size, max_step_size,
-                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, ray_list, n_list, grid_bits};
+                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, ray_list, n_list, grid_bits, dn.a};
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cells = (int64_t)rx * ry * rz;
     const size_t smem = (size_t)((cells + 31) / 32) * 4;
     const bool use_smem = (batch_inds == nullptr) && smem <= 96 * 1024;
     const unsigned grid = wave_grid(ray_list ? n_list : n_rays, 256, 2);
     if (use_smem) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_ray_marching<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_set = true;
-        }
+        opt_in_smem(k_ray_marching<true>, 96 * 1024);
         k_ray_marching<true><<<grid, 256, smem, s>>>(a);
     } else {
         k_ray_marching<false><<<grid, 256, 0, s>>>(a);

@@ -19,8 +19,9 @@ inline unsigned pack_grid(int64_t n_packs) { return wave_grid(n_packs * 32, kNB,
 
 __global__ void __launch_bounds__(kNB)
 k_upsample_cdf(const float *__restrict__ sdf, const float *__restrict__ dep, const int64_t *__restrict__ pi, int64_t n_packs, float inv_s,
-               int use_estimate, float eps, float thre, float *__restrict__ cdf) {
+               int use_estimate, float eps, float thre, float *__restrict__ cdf, const int64_t *__restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
+    n_packs = eff_n(n_packs, n_dev);
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
         float T = 1.f, carry = 0.f, last_excl = 0.f;
@@ -49,7 +50,8 @@ k_upsample_cdf(const float *__restrict__ sdf, const float *__restrict__ dep, con
 // inverse-cdf sampling at u[0..n_s) shared by all packs (kernel_packed_invert_cdf semantics, pack_ops_cuda.cu:1634-1682)
 __global__ void __launch_bounds__(256)
 k_invert_cdf_shared_u(const float *__restrict__ bins, const float *__restrict__ cdfs, const float *__restrict__ u, const int64_t *__restrict__ pi,
-                      int64_t n_packs, int n_s, float *__restrict__ samples) {
+                      int64_t n_packs, int n_s, float *__restrict__ samples, const int64_t *__restrict__ n_dev) {
+    n_packs = eff_n(n_packs, n_dev);
     const int64_t total = n_packs * n_s, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
         const int64_t p = t / n_s;
@@ -76,9 +78,15 @@ k_invert_cdf_shared_u(const float *__restrict__ bins, const float *__restrict__ 
 // ------------------------------------------------------------------------------------------------ render alpha (+ compression)
 __global__ void __launch_bounds__(kNB)
 k_neus_alpha_fwd(const float *__restrict__ sdf, const int64_t *__restrict__ pi, int64_t n_packs, const float *__restrict__ inv_s_p, float eps,
-                 float thre, float *__restrict__ alpha, uint8_t *__restrict__ selector, int32_t *__restrict__ num_steps) {
+                 float thre, float *__restrict__ alpha, uint8_t *__restrict__ selector, int32_t *__restrict__ num_steps,
+                 const int64_t *__restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
     const float inv_s = inv_s_p[0];
+    if (n_dev) {                                          // capacity > live packs: the packs in between keep nothing
+        const int64_t live = eff_n(n_packs, n_dev);
+        for (int64_t p = live + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_packs; p += (int64_t)gridDim.x * blockDim.x) num_steps[p] = 0;
+        n_packs = live;
+    }
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
         float T = 1.f;
@@ -100,9 +108,10 @@ k_neus_alpha_fwd(const float *__restrict__ sdf, const int64_t *__restrict__ pi, 
 //   d alpha_i / d c_i = (c_{i+1} + e) / (c_i + e)^2 ,  d alpha_i / d c_{i+1} = -1 / (c_i + e)   (where the clamp is inactive: raw >= 0)
 __global__ void __launch_bounds__(kNB)
 k_neus_alpha_bwd(const float *__restrict__ sdf, const int64_t *__restrict__ pi, int64_t n_packs, const float *__restrict__ inv_s_p,
-                 const float *__restrict__ d_alpha, float *__restrict__ d_sdf, float *__restrict__ d_inv_s) {
+                 const float *__restrict__ d_alpha, float *__restrict__ d_sdf, float *__restrict__ d_inv_s, const int64_t *__restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
     const float inv_s = inv_s_p[0];
+    n_packs = eff_n(n_packs, n_dev);
     float acc_invs = 0.f;
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
@@ -135,8 +144,10 @@ k_neus_alpha_bwd(const float *__restrict__ sdf, const int64_t *__restrict__ pi, 
 __global__ void __launch_bounds__(kNB)
 k_composite_fwd(const float *__restrict__ alpha, const float *__restrict__ t, const float *__restrict__ rgb, const float *__restrict__ nab,
                 const int64_t *__restrict__ pi, int64_t n_packs, float eps, float thre, int normalize_depth, const int64_t *__restrict__ ray_index,
-                float *__restrict__ vw, float *__restrict__ mask, float *__restrict__ depth, float *__restrict__ rgb_out, float *__restrict__ nab_out) {
+                float *__restrict__ vw, float *__restrict__ mask, float *__restrict__ depth, float *__restrict__ rgb_out, float *__restrict__ nab_out,
+                const int64_t *__restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
+    n_packs = eff_n(n_packs, n_dev);
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
         float T = 1.f;
@@ -176,8 +187,10 @@ k_composite_bwd(const float *__restrict__ alpha, const float *__restrict__ t, co
                 const float *__restrict__ vw, const int64_t *__restrict__ pi, int64_t n_packs, float eps, float thre, int normalize_depth,
                 const float *__restrict__ mask, const float *__restrict__ depth, const float *__restrict__ g_mask, const float *__restrict__ g_depth,
                 const float *__restrict__ g_rgb, const float *__restrict__ g_nab, const float *__restrict__ g_vw_ext,
-                const int64_t *__restrict__ ray_index, float *__restrict__ d_alpha, float *__restrict__ d_rgb, float *__restrict__ d_nab) {
+                const int64_t *__restrict__ ray_index, float *__restrict__ d_alpha, float *__restrict__ d_rgb, float *__restrict__ d_nab,
+                const int64_t *__restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
+    n_packs = eff_n(n_packs, n_dev);
     for (int64_t p = gwarp(); p < n_packs; p += nwarps()) {
         const int64_t b = pi[2 * p], n = pi[2 * p + 1];
         const int64_t o = ray_index ? ray_index[p] : p;
@@ -238,44 +251,49 @@ using namespace nsb;
 
 extern "C" int nsb_neus_upsample_cdf(const float *sdf, const float *depth, const int64_t *pack_infos, int64_t n_packs, float inv_s,
                                      int use_estimate_alpha, float early_stop_eps, float alpha_thre, float *cdf, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0) return 0;
     NSB_REQUIRE(sdf && depth && pack_infos && cdf, "nsb_neus_upsample_cdf: NULL argument");
-    k_upsample_cdf<<<pack_grid(n_packs), kNB, 0, STREAM>>>(sdf, depth, pack_infos, n_packs, inv_s, use_estimate_alpha, early_stop_eps, alpha_thre, cdf);
+    k_upsample_cdf<<<pack_grid(n_packs), kNB, 0, STREAM>>>(sdf, depth, pack_infos, n_packs, inv_s, use_estimate_alpha, early_stop_eps, alpha_thre, cdf, dn.a);
     return check_launch("nsb_neus_upsample_cdf");
 }
 
 extern "C" int nsb_packed_invert_cdf_shared_u(const float *bins, const float *cdfs, const float *u, const int64_t *pack_infos, int64_t n_packs,
                                               int32_t n_samples, float *samples, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0 || n_samples == 0) return 0;
     NSB_REQUIRE(bins && cdfs && u && pack_infos && samples, "nsb_packed_invert_cdf_shared_u: NULL argument");
-    k_invert_cdf_shared_u<<<wave_grid(n_packs * n_samples, 256, 8), 256, 0, STREAM>>>(bins, cdfs, u, pack_infos, n_packs, n_samples, samples);
+    k_invert_cdf_shared_u<<<wave_grid(n_packs * n_samples, 256, 8), 256, 0, STREAM>>>(bins, cdfs, u, pack_infos, n_packs, n_samples, samples, dn.a);
     return check_launch("nsb_packed_invert_cdf_shared_u");
 }
 
 extern "C" int nsb_neus_alpha_forward(const float *sdf, const int64_t *pack_infos, int64_t n_packs, const float *inv_s_dev, float early_stop_eps,
                                       float alpha_thre, float *alpha, uint8_t *selector, int32_t *num_steps, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0) return 0;
     NSB_REQUIRE(sdf && pack_infos && inv_s_dev && alpha && selector && num_steps, "nsb_neus_alpha_forward: NULL argument");
-    k_neus_alpha_fwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(sdf, pack_infos, n_packs, inv_s_dev, early_stop_eps, alpha_thre, alpha, selector, num_steps);
+    k_neus_alpha_fwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(sdf, pack_infos, n_packs, inv_s_dev, early_stop_eps, alpha_thre, alpha, selector, num_steps, dn.a);
     return check_launch("nsb_neus_alpha_forward");
 }
 
 extern "C" int nsb_neus_alpha_backward(const float *sdf, const int64_t *pack_infos, int64_t n_packs, const float *inv_s_dev, const float *d_alpha,
                                        float *d_sdf, float *d_inv_s, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0) return 0;
     NSB_REQUIRE(sdf && pack_infos && inv_s_dev && d_alpha && d_sdf && d_inv_s, "nsb_neus_alpha_backward: NULL argument");
-    k_neus_alpha_bwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(sdf, pack_infos, n_packs, inv_s_dev, d_alpha, d_sdf, d_inv_s);
+    k_neus_alpha_bwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(sdf, pack_infos, n_packs, inv_s_dev, d_alpha, d_sdf, d_inv_s, dn.a);
     return check_launch("nsb_neus_alpha_backward");
 }
 
 extern "C" int nsb_composite_forward(const float *alpha, const float *t, const float *rgb, const float *nablas, const int64_t *pack_infos,
                                      int64_t n_packs, float early_stop_eps, float alpha_thre, int normalize_depth, const int64_t *ray_index,
                                      float *vw, float *mask, float *depth, float *rgb_out, float *nablas_out, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0) return 0;
     NSB_REQUIRE(alpha && t && pack_infos && vw && mask && depth, "nsb_composite_forward: NULL argument");
     NSB_REQUIRE((!rgb || rgb_out) && (!nablas || nablas_out), "nsb_composite_forward: missing output buffer");
     k_composite_fwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(alpha, t, rgb, nablas, pack_infos, n_packs, early_stop_eps, alpha_thre, normalize_depth,
-                                                            ray_index, vw, mask, depth, rgb_out, nablas_out);
+                                                            ray_index, vw, mask, depth, rgb_out, nablas_out, dn.a);
     return check_launch("nsb_composite_forward");
 }
 
@@ -284,10 +302,11 @@ extern "C" int nsb_composite_backward(const float *alpha, const float *t, const 
                                       const float *mask, const float *depth, const float *g_mask, const float *g_depth, const float *g_rgb,
                                       const float *g_nablas, const float *g_vw, const int64_t *ray_index, float *d_alpha, float *d_rgb,
                                       float *d_nablas, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0) return 0;
     NSB_REQUIRE(alpha && t && vw && pack_infos && mask && depth && d_alpha, "nsb_composite_backward: NULL argument");
     NSB_REQUIRE((!rgb || d_rgb) && (!nablas || d_nablas), "nsb_composite_backward: missing output buffer");
     k_composite_bwd<<<pack_grid(n_packs), kNB, 0, STREAM>>>(alpha, t, rgb, nablas, vw, pack_infos, n_packs, early_stop_eps, alpha_thre, normalize_depth,
-                                                            mask, depth, g_mask, g_depth, g_rgb, g_nablas, g_vw, ray_index, d_alpha, d_rgb, d_nablas);
+                                                            mask, depth, g_mask, g_depth, g_rgb, g_nablas, g_vw, ray_index, d_alpha, d_rgb, d_nablas, dn.a);
     return check_launch("nsb_composite_backward");
 }

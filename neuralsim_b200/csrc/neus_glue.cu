@@ -150,8 +150,9 @@ constexpr int kMergeWarps = 8;
 __global__ void __launch_bounds__(kMergeWarps * 32)
 k_merge_vals(const float *__restrict__ dep_a, const float *__restrict__ sdf_a, const int64_t *__restrict__ pi_a, const float *__restrict__ dep_b,
              const float *__restrict__ sdf_b, int64_t n_packs, int nb, float *__restrict__ dep_m, float *__restrict__ sdf_m,
-             int64_t *__restrict__ pi_m) {
+             int64_t *__restrict__ pi_m, const int64_t *__restrict__ n_dev) {
     extern __shared__ float s_b[];                        // [warps][nb]
+    n_packs = eff_n(n_packs, n_dev);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float *bb = s_b + w * nb;
     for (int64_t p = gwarp_(); p < n_packs; p += nwarps_()) {
@@ -204,8 +205,11 @@ __device__ __forceinline__ int count_less(const float *a, int n, float v, bool o
 __global__ void __launch_bounds__(kAsmWarps * 32)
 k_assemble_boundary(const float *__restrict__ coarse, int64_t n_rays, int nc, const int64_t *__restrict__ ridx_hit, int64_t n_hit,
                     const float *__restrict__ fine, int nf, const AsmRuns runs, float *__restrict__ d1, float *__restrict__ mid,
-                    int64_t *__restrict__ ridx_all, int64_t *__restrict__ pack_infos) {
+                    int64_t *__restrict__ ridx_all, int64_t *__restrict__ pack_infos, const int64_t *__restrict__ n_rays_dev,
+                    const int64_t *__restrict__ n_hit_dev) {
     extern __shared__ float s_v[];                        // [warps][2][nc + nf]
+    n_rays = eff_n(n_rays, n_rays_dev);
+    n_hit = eff_n(n_hit, n_hit_dev);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cap = nc + nf;
     float *raw = s_v + (size_t)w * 2 * cap, *srt = raw + cap;
     for (int64_t r = gwarp_(); r < n_rays; r += nwarps_()) {
@@ -262,8 +266,9 @@ __global__ void __launch_bounds__(256)
 k_compact_samples(const uint8_t *__restrict__ selector, const int64_t *__restrict__ pi, const int32_t *__restrict__ first_out,
                   const int32_t *__restrict__ kept, int64_t n_packs, const int64_t *__restrict__ ridx_all, const float *__restrict__ t,
                   const float *__restrict__ alpha, int64_t *__restrict__ pidx, int64_t *__restrict__ ridx_c, float *__restrict__ t_c,
-                  float *__restrict__ alpha_c) {
+                  float *__restrict__ alpha_c, const int64_t *__restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
+    n_packs = eff_n(n_packs, n_dev);
     for (int64_t p = gwarp_(); p < n_packs; p += nwarps_()) {
         const int32_t kp = kept[p];
         if (kp == 0) continue;
@@ -290,7 +295,8 @@ k_compact_samples(const uint8_t *__restrict__ selector, const int64_t *__restric
 
 // dst[idx[j]] = src[j]  (adjoint of a gather with unique indices; dst is zero-filled by the caller)
 __global__ void __launch_bounds__(256)
-k_scatter_f32(const float *__restrict__ src, const int64_t *__restrict__ idx, int64_t n, float *__restrict__ dst) {
+k_scatter_f32(const float *__restrict__ src, const int64_t *__restrict__ idx, int64_t n, float *__restrict__ dst, const int64_t *__restrict__ n_dev) {
+    n = eff_n(n, n_dev);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) dst[idx[j]] = src[j];
 }
@@ -356,7 +362,8 @@ k_ray_test_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays
 __global__ void __launch_bounds__(256)
 k_gather_rays(const int64_t *__restrict__ idx, int64_t n, const float *__restrict__ o_n, const float *__restrict__ d_n, const float *__restrict__ near,
               const float *__restrict__ far, float *__restrict__ o_c, float *__restrict__ d_c, float *__restrict__ near_c, float *__restrict__ far_c,
-              const float *__restrict__ extra, float *__restrict__ extra_c, int extra_cols) {
+              const float *__restrict__ extra, float *__restrict__ extra_c, int extra_cols, const int64_t *__restrict__ n_dev) {
+    n = eff_n(n, n_dev);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         const int64_t i = idx[j];
@@ -368,10 +375,65 @@ k_gather_rays(const int64_t *__restrict__ idx, int64_t n, const float *__restric
     }
 }
 
+// flag[i] = (v[i] != 0) for i < n_eff, 0 up to the capacity n: the input of the scan that compacts the samples with a non-zero cotangent
+__global__ void __launch_bounds__(256)
+k_flag_nonzero(const float *__restrict__ v, int64_t n, int32_t *__restrict__ flag, const int64_t *__restrict__ n_dev) {
+    const int64_t ne = eff_n(n, n_dev), stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flag[i] = (i < ne && v[i] != 0.f) ? 1 : 0;
+}
+
+// Derived sizes of one NeuS query, kept on the device (nsb_query_counts; slot layout in include/neuralsim_b200.h).
+__global__ void k_query_counts(int64_t *__restrict__ c, int phase, int nc, int n_stage, int nf0, int nf1, int nf2, int nf3, int64_t march_cap,
+                               int64_t kept_cap) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (phase == 0) {                                     // after the scan of the march counts: c[3] = M, c[4] = n_hit
+        const int nf[4] = {nf0, nf1, nf2, nf3};
+        int64_t M = c[3], nh = c[4];
+        int64_t worst = M, tot = 0;
+        for (int q = 0; q + 1 < n_stage; ++q) worst += nh * nf[q];        // the merged buffers grow by nf_q samples per hit ray and stage
+        if (worst > march_cap) { c[20] |= 1; M = 0; nh = 0; }             // arena too small: the step renders nothing and says so
+        c[12] = M;
+        c[13] = nh;
+        int64_t merged = M;
+        for (int q = 0; q < 4; ++q) {
+            c[14 + q] = q < n_stage ? nh * nf[q] : 0;
+            if (q < n_stage) tot += nf[q];
+            if (q + 1 < n_stage) merged += nh * nf[q];
+            c[22 + q] = merged;                           // samples in the merged buffer after stage q
+        }
+        c[18] = c[0] * nc + nh * tot;                      // S: boundary samples
+    } else {                                              // after the scan of the kept counts: c[6] = K, c[7] = rays that keep samples
+        int64_t K = c[6], pu = c[7];
+        const bool fits = K <= kept_cap;
+        if (!fits) { c[20] |= 2; K = 0; pu = 0; }
+        c[19] = K;
+        c[21] = pu;
+        c[26] = fits ? c[0] : 0;                           // packs the compaction of the kept samples may walk
+    }
+}
+
 }  // namespace nsb
 
 using namespace nsb;
 #define STREAM ((cudaStream_t)stream)
+
+extern "C" int nsb_flag_nonzero(const float *v, int64_t n, int32_t *flag, void *stream) {
+    const DevCounts dn = take_counts();
+    if (n == 0) return 0;
+    NSB_REQUIRE(v && flag, "nsb_flag_nonzero: NULL argument");
+    k_flag_nonzero<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(v, n, flag, dn.a);
+    return check_launch("nsb_flag_nonzero");
+}
+
+extern "C" int nsb_query_counts(int64_t *counts, int32_t phase, int32_t n_coarse, const int32_t *n_fine_host, int32_t n_stage, int64_t march_cap,
+                                int64_t kept_cap, void *stream) {
+    NSB_REQUIRE(counts, "nsb_query_counts: counts is NULL");
+    NSB_REQUIRE(n_stage >= 0 && n_stage <= 4 && (n_stage == 0 || n_fine_host), "nsb_query_counts: at most 4 up-sampling stages");
+    int nf[4] = {0, 0, 0, 0};
+    for (int q = 0; q < n_stage; ++q) nf[q] = n_fine_host[q];
+    k_query_counts<<<1, 32, 0, STREAM>>>(counts, phase, n_coarse, n_stage, nf[0], nf[1], nf[2], nf[3], march_cap, kept_cap);
+    return check_launch("nsb_query_counts");
+}
 
 extern "C" int64_t nsb_scan_workspace_bytes(void) { return (int64_t)sizeof(ScanWs); }
 
@@ -393,26 +455,27 @@ extern "C" int nsb_scan_counts(const int32_t *counts, int64_t n, int32_t *first,
 
 extern "C" int nsb_merge_sorted_vals(const float *dep_a, const float *sdf_a, const int64_t *pack_infos_a, const float *dep_b, const float *sdf_b,
                                      int64_t n_packs, int32_t n_b, float *dep_m, float *sdf_m, int64_t *pack_infos_m, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0) return 0;
     NSB_REQUIRE(dep_a && pack_infos_a && dep_b && dep_m && pack_infos_m, "nsb_merge_sorted_vals: NULL argument");
     NSB_REQUIRE((sdf_m == nullptr) || (sdf_a && sdf_b), "nsb_merge_sorted_vals: sdf_m needs sdf_a and sdf_b");
     NSB_REQUIRE(n_b > 0 && n_b <= 1024, "nsb_merge_sorted_vals: n_b must be in [1, 1024]");
     const size_t smem = (size_t)kMergeWarps * n_b * sizeof(float);
     k_merge_vals<<<wave_grid(n_packs * 32, kMergeWarps * 32, 8), kMergeWarps * 32, smem, STREAM>>>(dep_a, sdf_a, pack_infos_a, dep_b, sdf_b, n_packs, n_b,
-                                                                                                 dep_m, sdf_m, pack_infos_m);
+                                                                                                 dep_m, sdf_m, pack_infos_m, dn.a);
     return check_launch("nsb_merge_sorted_vals");
 }
 
 extern "C" int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_t n_coarse, const int64_t *ridx_hit, int64_t n_hit, const float *fine,
                                      int32_t n_fine, const int32_t *run_len, int32_t n_runs, float *d1, float *mid, int64_t *ridx_all,
                                      int64_t *pack_infos, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_rays == 0) return 0;
     NSB_REQUIRE(coarse && d1 && mid && ridx_all && pack_infos, "nsb_assemble_boundary: NULL argument");
     NSB_REQUIRE(n_hit == 0 || (ridx_hit && fine), "nsb_assemble_boundary: hit rays need ridx_hit and fine");
     NSB_REQUIRE(n_coarse > 0 && n_fine >= 0 && n_coarse + n_fine <= 1024, "nsb_assemble_boundary: n_coarse + n_fine must be <= 1024");
     const size_t smem = (size_t)kAsmWarps * 2 * (n_coarse + n_fine) * sizeof(float);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_assemble_boundary, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    opt_in_smem(k_assemble_boundary, 96 * 1024);
     NSB_REQUIRE(smem <= 96 * 1024, "nsb_assemble_boundary: too many samples per ray for shared memory");
     AsmRuns runs{};
     NSB_REQUIRE(n_runs >= 0 && n_runs <= kAsmMaxRuns && (n_runs == 0 || run_len), "nsb_assemble_boundary: at most %d sorted runs", kAsmMaxRuns);
@@ -421,25 +484,27 @@ extern "C" int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_
     runs.n = n_runs;
     NSB_REQUIRE(tot == n_fine, "nsb_assemble_boundary: run lengths must add up to n_fine");
     k_assemble_boundary<<<wave_grid(n_rays * 32, kAsmWarps * 32, 8), kAsmWarps * 32, smem, STREAM>>>(coarse, n_rays, n_coarse, ridx_hit, n_hit, fine, n_fine,
-                                                                                                  runs, d1, mid, ridx_all, pack_infos);
+                                                                                                  runs, d1, mid, ridx_all, pack_infos, dn.a, dn.b);
     return check_launch("nsb_assemble_boundary");
 }
 
 extern "C" int nsb_compact_samples(const uint8_t *selector, const int64_t *pack_infos, const int32_t *first_out, const int32_t *kept, int64_t n_packs,
                                    const int64_t *ridx_all, const float *t, const float *alpha, int64_t *pidx, int64_t *ridx_c, float *t_c,
                                    float *alpha_c, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_packs == 0) return 0;
     NSB_REQUIRE(selector && pack_infos && first_out && kept && ridx_all && t && alpha && pidx && ridx_c && t_c && alpha_c,
                 "nsb_compact_samples: NULL argument");
     k_compact_samples<<<wave_grid(n_packs * 32, 256, 8), 256, 0, STREAM>>>(selector, pack_infos, first_out, kept, n_packs, ridx_all, t, alpha, pidx, ridx_c,
-                                                                          t_c, alpha_c);
+                                                                          t_c, alpha_c, dn.a);
     return check_launch("nsb_compact_samples");
 }
 
 extern "C" int nsb_scatter_f32(const float *src, const int64_t *idx, int64_t n, float *dst, void *stream) {
+    const DevCounts dn = take_counts();
     if (n == 0) return 0;
     NSB_REQUIRE(src && idx && dst, "nsb_scatter_f32: NULL argument");
-    k_scatter_f32<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(src, idx, n, dst);
+    k_scatter_f32<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(src, idx, n, dst, dn.a);
     return check_launch("nsb_scatter_f32");
 }
 
@@ -455,9 +520,10 @@ extern "C" int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64
 
 extern "C" int nsb_gather_rays(const int64_t *idx, int64_t n, const float *o_n, const float *d_n, const float *near, const float *far, float *o_c,
                                float *d_c, float *near_c, float *far_c, const float *extra, float *extra_c, int32_t extra_cols, void *stream) {
+    const DevCounts dn = take_counts();
     if (n == 0) return 0;
     NSB_REQUIRE(idx && o_n && d_n && near && far && o_c && d_c && near_c && far_c, "nsb_gather_rays: NULL argument");
     NSB_REQUIRE(extra_cols == 0 || (extra && extra_c), "nsb_gather_rays: extra payload needs both pointers");
-    k_gather_rays<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(idx, n, o_n, d_n, near, far, o_c, d_c, near_c, far_c, extra, extra_c, extra_cols);
+    k_gather_rays<<<wave_grid(n, 256, 8), 256, 0, STREAM>>>(idx, n, o_n, d_n, near, far, o_c, d_c, near_c, far_c, extra, extra_c, extra_cols, dn.a);
     return check_launch("nsb_gather_rays");
 }

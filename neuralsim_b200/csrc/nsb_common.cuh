@@ -34,14 +34,41 @@ inline int check_launch(const char *what) {
         }                             \
     } while (0)
 
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+// per DEVICE (a single process may drive several GPUs: render_parallel's worker threads)
 inline int sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[64];
+    const int dev = current_device() & 63;
+    int n = cache[dev].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
+    return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and the call is not free
+template <typename K>
+inline void opt_in_smem(K kernel, int bytes) {
+    static std::atomic<int> done[64];
+    const int dev = current_device() & 63;
+    if (done[dev].load(std::memory_order_relaxed) >= bytes) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done[dev].store(bytes, std::memory_order_relaxed);
+}
+
+// Device-resident counts (nsb_bind_device_counts, include/neuralsim_b200.h): the entry points that support them take the binding of the
+// calling thread; the kernels then process min(n_arg, *count) items, n_arg being the capacity the launch was sized for.
+struct DevCounts { const int64_t *a, *b; };
+DevCounts take_counts();
+__device__ __forceinline__ int64_t eff_n(int64_t n, const int64_t *__restrict__ nd) {
+    if (nd) { const int64_t v = *nd; return v < n ? (v < 0 ? 0 : v) : n; }
     return n;
 }
 
