@@ -244,21 +244,32 @@ def use_reference_cuda_kernels():
 
 
 # ---------------------------------------------------------------------------------------------- main arm
+def stats_of(ts):
+    a = np.asarray(ts, dtype=np.float64)
+    return dict(mean=float(a.mean()), median=float(np.median(a)), min=float(a.min()), max=float(a.max()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
-    ap.add_argument("--rayschunk", type=int, default=H * W, help="rays per render call (default: the whole frame in one call)")
-    ap.add_argument("--rays", type=int, default=H * W, help="rays per step (default: the full 800x600 frame)")
+    ap.add_argument("--mode", default="graph", choices=["graph", "static", "host"],
+                    help="graph: the whole fwd+bwd step is ONE CUDA-graph launch (sizes stay on the device; default).  static: the same step launched "
+                         "kernel by kernel.  host: the host-sized path (three host reads per step; round-1 behaviour)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank renders its own 800x600 frame; strong: the ranks share ONE frame (480000 / N rays each)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--rayschunk", type=int, default=0, help="host mode only: rays per render call (0 = the whole batch in one call)")
+    ap.add_argument("--rays", type=int, default=H * W, help="rays per step and GPU (default: the full 800x600 frame)")
     ap.add_argument("--random-rays", action="store_true", help="draw the --rays rays of every pose as random pixels (a training batch) instead of the first rows")
     ap.add_argument("--collect-samples", action="store_true", help="accel.update_from_samples_cfg = {} as in the shipped training config: every "
                     "training-time SDF query also feeds the occupancy grid's evidence buffer (in-kernel here, torch_scatter in the reference)")
-    ap.add_argument("--clock-period-ms", type=int, default=100, help="0 = no clock sampler (diagnostics); any other value: sample between steps")
+    ap.add_argument("--clock-period-ms", type=int, default=100, help="0 = no clock sampler (diagnostics)")
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--dump-render", default=None, help="(internal) save the rendered buffers of view 0 to this file")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -278,40 +289,92 @@ def main():
 
     from neuralsim_b200 import _lib
     from neuralsim_b200.renderer import SingleVolumeRenderer
-    if args.impl == "reference-cuda" and not use_reference_cuda_kernels():
-        raise SystemExit("bench.py: oracle/_ref is not built (python oracle/build_ref.py in the build container)")
-    model = build_model(device, collect_samples=args.collect_samples).train()
-    renderer = SingleVolumeRenderer(dict(near=0.01, rayschunk=0)).train()
+    from neuralsim_b200.graphics.neus_static import StaticFrame
+    mode = args.mode
+    if args.impl == "reference-cuda":
+        if not use_reference_cuda_kernels():
+            raise SystemExit("bench.py: oracle/_ref is not built (python oracle/build_ref.py in the build container)")
+        mode = "host"
+    if args.workload == "cfg3":
+        import bench_cfg3
+        model = bench_cfg3.build_model(device).train()
+        make_views, near = bench_cfg3.make_views, bench_cfg3.NEAR
+        with_rgb_note = "8192 camera + 8192 LiDAR-like rays per step"
+    else:
+        model = build_model(device, collect_samples=args.collect_samples).train()
+        make_views, near = None, 0.01
+    renderer = SingleVolumeRenderer(dict(near=near, rayschunk=0)).train()
     flat, params = flat_grad_views(model)
     n_rays = args.rays
+    if args.scaling == "strong":
+        n_rays = (args.rays + world - 1) // world
     views_host, views_dev = [], []
     for k in range(N_VIEWS):
-        o, d = pinhole_rays(H, W, orbit((k * world + rank) % (N_VIEWS * world), N_VIEWS * world))
-        if args.random_rays:
-            sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(1000 + k))[:n_rays]
-            o, d = o[sel].contiguous(), d[sel].contiguous()
+        if make_views is not None:
+            o, d = make_views(k, n_rays, rank, world)
+        elif args.scaling == "strong":           # ONE frame per step, its rows dealt to the ranks in contiguous blocks
+            o, d = pinhole_rays(H, W, orbit(k, N_VIEWS))
+            if args.random_rays:
+                sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(1000 + k))[:args.rays]
+                o, d = o[sel], d[sel]
+            o, d = o[rank * n_rays:(rank + 1) * n_rays].contiguous(), d[rank * n_rays:(rank + 1) * n_rays].contiguous()
+            if o.shape[0] < n_rays:                # the last rank's block is padded with its own last ray
+                pad = n_rays - o.shape[0]
+                o, d = torch.cat([o, o[-1:].expand(pad, 3)]).contiguous(), torch.cat([d, d[-1:].expand(pad, 3)]).contiguous()
         else:
-            o, d = o[:n_rays].contiguous(), d[:n_rays].contiguous()
+            o, d = pinhole_rays(H, W, orbit((k * world + rank) % (N_VIEWS * world), N_VIEWS * world))
+            if args.random_rays:
+                sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(1000 + k))[:n_rays]
+                o, d = o[sel].contiguous(), d[sel].contiguous()
+            else:
+                o, d = o[:n_rays].contiguous(), d[:n_rays].contiguous()
         views_host.append((o.pin_memory(), d.pin_memory()))
         views_dev.append((o.to(device), d.to(device)))
-    h_appear = torch.zeros(args.rayschunk, 4, device=device)
+    n_appear = 4
+    h_appear = torch.zeros(n_rays, n_appear, device=device)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
-    stats = dict(samples=0, points=0)
+    chunk = args.rayschunk if args.rayschunk > 0 else n_rays
+    keys = ("rgb_volume", "depth_volume", "normals_volume", "mask_volume")
+    out_host = {"rgb_volume": torch.zeros(n_rays, 3).pin_memory(), "depth_volume": torch.zeros(n_rays).pin_memory(),
+                "normals_volume": torch.zeros(n_rays, 3).pin_memory(), "mask_volume": torch.zeros(n_rays).pin_memory()}
+    loss_host = torch.zeros((), pin_memory=True)
+    d2h_bytes = int(sum(v.numel() * 4 for v in out_host.values()) + 4)
+
+    # ------------------------------------------------------------------ the step
+    frame = None
+    if mode in ("graph", "static"):
+        # flat.zero_() is part of the step (and of the graph); every size stays on the device; ONE launch per step in graph mode
+        frame = StaticFrame(model, n_rays, loss_fn=loss_of, near=near, use_graph=(mode == "graph"), pre_hook=flat.zero_)
+        frame.rays_o.copy_(views_dev[0][0]); frame.rays_d.copy_(views_dev[0][1])
+        frame._size()                               # arenas from view 0 ...
+        for k in range(1, N_VIEWS):                 # ... grown to the largest of the poses this run renders
+            frame.rays_o.copy_(views_dev[k][0]); frame.rays_d.copy_(views_dev[k][1])
+            frame._size()
+        frame.capture()
+
+    last = {}
 
     def step(o, d):
-        """fwd+bwd of one frame, chunked over rays; gradients accumulate into the flat buffer."""
-        flat.zero_()
-        total = torch.zeros((), device=device)
-        for s in range(0, n_rays, args.rayschunk):
-            e = min(s + args.rayschunk, n_rays)
-            out = renderer.render(model, o[s:e], d[s:e], rays_h_appear=h_appear[:e - s])["rendered"]
-            loss = loss_of(out) * ((e - s) / n_rays)
-            if loss.requires_grad:             # a chunk whose rays all miss the object renders constants
-                loss.backward()
-            total += loss.detach()
+        """fwd+bwd of one batch of rays; gradients land in the flat buffer.  -> (loss, rendered)"""
+        if frame is not None:
+            loss = frame.step(o, d, None)
+            rendered = frame.rendered
+        else:
+            flat.zero_()
+            total = torch.zeros((), device=device)
+            rendered = None
+            for s0 in range(0, n_rays, chunk):
+                e = min(s0 + chunk, n_rays)
+                rendered = renderer.render(model, o[s0:e], d[s0:e], rays_h_appear=h_appear[:e - s0])["rendered"]
+                loss = loss_of(rendered) * ((e - s0) / n_rays)
+                if loss.requires_grad:             # a chunk whose rays all miss the object renders constants
+                    loss.backward()
+                total += loss.detach()
+            loss = total
         if world > 1:
-            dist.all_reduce(flat)            # the one collective of a step: sum of the flat gradient
-        return total
+            dist.all_reduce(flat)                # the one collective of a step: sum of the flat gradient
+        last["rendered"] = rendered
+        return loss
 
     def timed(fn, k, sampler=None):
         evs = []
@@ -325,19 +388,23 @@ def main():
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
-    # every camera pose of the timed loops has been rendered once during warm-up (the caching allocator has seen its tensor sizes)
     n_views = max(1, min(N_VIEWS, args.warmup))
 
     def resident(i):
         o, d = views_dev[i % n_views]
         return step(o, d)
 
-    loss_host = torch.zeros((), pin_memory=True)
-
     def e2e(i):
         oh, dh = views_host[i % n_views]
-        o, d = oh.to(device, non_blocking=True), dh.to(device, non_blocking=True)     # H2D of the step's rays
-        loss_host.copy_(step(o, d), non_blocking=True)                                # D2H of the step's result
+        if frame is not None:
+            loss = step(oh, dh)                                                       # H2D of the step's rays straight into the graph's inputs
+        else:
+            loss = step(oh.to(device, non_blocking=True), dh.to(device, non_blocking=True))
+        rendered = last["rendered"]
+        if rendered is not None and chunk >= n_rays:
+            for kk in keys:                                                           # D2H of the rendered buffers (15.4 MB for a frame) ...
+                out_host[kk].copy_(rendered[kk], non_blocking=True)
+        loss_host.copy_(loss, non_blocking=True)                                      # ... and of the loss
         torch.cuda.current_stream().synchronize()
 
     with ClockSampler(local, args.clock_period_ms) as clocks:          # see the class: one clock query after the last timed launch
@@ -346,26 +413,61 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        launches0 = _lib.launch_count()
         import gc
         gc.collect()
-        gc.disable()                           # no collector pause inside a 15 ms step; re-enabled right after the timed loops
-        t_e2e = timed(e2e, args.steps)       # the headline loop runs first: nothing has queried the GPU's management interface yet
+        gc.disable()                           # no collector pause inside a step; re-enabled right after the timed loops
+        t_e2e = timed(e2e, args.steps)
         if world > 1:
             dist.barrier()
-        launches0 = _lib.launch_count()
+        torch.cuda.synchronize()
         t_res = timed(resident, args.steps, clocks)      # ... and the one clock query comes after its last launch (see ClockSampler)
-        launches = _lib.launch_count() - launches0
         gc.enable()
-        time.sleep(0.5)
-        # a separate, instrumented pass for the roofline: CUDA events around every launch of our kernels (not part of `value`)
-        _lib.KERNEL_TIMER.enable()
-        t_inst = timed(resident, args.steps)
-        _lib.KERNEL_TIMER.disable()
-    ms = torch.tensor([sum(t_res) / args.steps, sum(t_e2e) / args.steps], device=device)
+        overflow = int(frame.counts()["overflow"]) if frame is not None else 0
+        # a separate, instrumented pass for the roofline: the same step launched kernel by kernel with CUDA events around every launch of
+        # the hash-gather kernels (not part of `value`); sizes are read back after every step to count the points that were processed
+        inst_steps = min(args.steps, 5)
+        points = dict(gather=0, marched=0, boundary=0, kept=0)
+        launches_per_step = None
+        if frame is not None:
+            inst = StaticFrame(model, n_rays, loss_fn=loss_of, near=near, use_graph=False, pre_hook=flat.zero_, march_cap=frame.march_cap,
+                               kept_cap=frame.kept_cap, coherent=frame.coherent)
+            inst.step(*views_dev[0])
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
+            inst.step(*views_dev[0])
+            launches_per_step = _lib.launch_count() - l0
+            _lib.KERNEL_TIMER.enable()
+            t_inst = []
+            for i in range(inst_steps):
+                flush_buf.fill_(i & 0xff)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); inst.step(*views_dev[i % n_views]); b.record()
+                torch.cuda.synchronize()
+                t_inst.append(a.elapsed_time(b))
+                c = inst.cnt.tolist()
+                stages = [c[14 + q] for q in range(4) if c[14 + q]]
+                fine_q = sum(stages[:-1]) if stages else 0         # the fine samples that are re-queried: every stage but the last
+                points["marched"] += c[12]; points["boundary"] += c[18]; points["kept"] += c[19]
+                points["gather"] += c[12] + fine_q + c[18]
+            _lib.KERNEL_TIMER.disable()
+        else:
+            l0 = _lib.launch_count()
+            _lib.KERNEL_TIMER.enable()
+            t_inst = timed(resident, inst_steps)
+            _lib.KERNEL_TIMER.disable()
+            launches_per_step = (_lib.launch_count() - l0) // max(inst_steps, 1)
+    st_res, st_e2e = stats_of(t_res), stats_of(t_e2e)
+    ms = torch.tensor([st_res["mean"], st_e2e["mean"], st_res["median"], st_e2e["median"]], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_res, ms_e2e = float(ms[0]), float(ms[1])
+    ms_res, ms_e2e, med_res, med_e2e = (float(x) for x in ms)
+    if args.dump_render and rank == 0:
+        with torch.no_grad():
+            model.eval()
+            o0, d0 = pinhole_rays(H, W, orbit(0, N_VIEWS))
+            out = SingleVolumeRenderer(dict(near=near)).eval().render(model, o0.to(device), d0.to(device), rays_h_appear=torch.zeros(o0.shape[0], n_appear, device=device))["rendered"]
+            torch.save({k: v.cpu() for k, v in out.items()}, args.dump_render)
+            model.train()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -378,11 +480,13 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     kt = _lib.KERNEL_TIMER.summary()
-    # the hash gather lives in three kernels: k_fused_sdf_tc (no-grad and autograd forward) and k_lotd_fwd (colour points)
+    # the hash gather of the SDF queries lives in k_fused_sdf_tc: the no-grad queries ("lotd_gather") and the boundary query ("fused_sdf_fwd")
     gather = None
     for key in ("fused_sdf_fwd", "lotd_gather"):
         if key in kt:
-            gather = kt[key] if gather is None else {k: gather[k] + kt[key][k] for k in gather}
+            gather = dict(kt[key]) if gather is None else {k: gather[k] + kt[key][k] for k in gather}
+    if gather and frame is not None:
+        gather["units"] = points["gather"]            # points actually processed (the launches are sized by capacity)
     traffic, traffic_note = None, None
     try:       # dram bytes of the dominant gather launch, from the committed ncu --set full capture (per launch, like `achieved`)
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
@@ -391,42 +495,75 @@ def main():
     except Exception:
         pass
     roof = None
-    if gather:
+    if gather and gather["ms"] > 0:
         achieved = gather["units"] * 512.0 / (gather["ms"] * 1e-3) / 1e9     # 512 B of table per encoded point
-        roof = {"kernel": "LoTD hash gather: k_fused_sdf_tc (gather + tcgen05 decoder) and k_lotd_fwd", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                "points_per_launch": gather["units"] / max(gather["launches"], 1), "launches": gather["launches"],
+        per_ms = {k: v["ms"] / inst_steps for k, v in kt.items()}
+        roof = {"kernel": "LoTD hash gather: k_fused_sdf_tc (gather + tcgen05 decoder), all no-grad and boundary SDF queries of the step", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": traffic_note, "points_per_launch": gather["units"] / max(gather["launches"], 1), "launches": gather["launches"],
                 "avg_launch_ms": gather["ms"] / max(gather["launches"], 1), "share_of_step": gather["ms"] / max(sum(t_inst), 1e-9),
-                "per_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kt.items()},
-                "per_kernel_points_per_step": {k: v["units"] / args.steps for k, v in kt.items()}}
+                "per_kernel_ms_per_step": per_ms, "points_per_step": {k: v / inst_steps for k, v in points.items()} if frame is not None else None,
+                "how": "CUDA events around every launch of these kernels in a separate kernel-by-kernel pass of the same step (events cannot sit inside the graph)"}
+    tot_rays = world * n_rays
     line = {
-        "metric": "Mrays/sec fwd+bwd", "value": world * n_rays / (ms_res * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "metric": "Mrays/sec fwd+bwd", "value": tot_rays / (ms_res * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": "cfg2", "model": "LoTDNeuS 16x2 LoTD (12.13M params) + 32-64-1 SDF MLP + 58-64-64-3 radiance MLP",
-                   "frame": "800x600", "rays_per_step_per_gpu": n_rays, "ray_order": "random pixels" if args.random_rays else "image rows", "collect_samples": bool(args.collect_samples), "rayschunk": args.rayschunk, "samples_per_ray": "<=116 boundary, <=1024 marched",
-                   "parallelism": f"dp{world} ray-shard, 1 all-reduce/step", "l2": "256 MiB L2 flush between steps; per-step working set >> 126 MB", "camera_poses": n_views},
-        "e2e": {"value": world * n_rays / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(2 * n_rays * 3 * 4), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof,
-        "step_ms": {"resident": [round(x, 3) for x in t_res], "e2e": [round(x, 3) for x in t_e2e]},
+        "median": {"ms_per_step": med_res, "value": tot_rays / (med_res * 1e-3) / 1e6, "e2e_ms_per_step": med_e2e, "e2e_value": tot_rays / (med_e2e * 1e-3) / 1e6},
+        "config": {"workload": args.workload, "model": "LoTDNeuS 16x2 LoTD (12.13M params) + 32-64-1 SDF MLP + 58-64-64-3 radiance MLP",
+                   "frame": "800x600", "rays_per_step_per_gpu": n_rays, "ray_order": "random pixels" if args.random_rays else "image rows",
+                   "collect_samples": bool(args.collect_samples), "mode": mode,
+                   "step": {"graph": "one CUDA-graph launch per step, no host read (sizes stay on the device)", "static": "kernel-by-kernel, no host read",
+                            "host": "kernel-by-kernel, three host reads per step"}[mode],
+                   "samples_per_ray": "<=116 boundary, <=1024 marched",
+                   "parallelism": f"dp{world} ray-shard ({args.scaling}), 1 all-reduce/step", "l2": "256 MiB L2 flush between steps; per-step working set >> 126 MB",
+                   "camera_poses": n_views, "arena_overflow": overflow,
+                   "arenas": {"march_cap": frame.march_cap, "kept_cap": frame.kept_cap} if frame is not None else None},
+        "e2e": {"value": tot_rays / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(2 * n_rays * 3 * 4), "d2h_bytes_per_step": d2h_bytes,
+                "what": "pinned-host rays H2D -> step -> rendered rgb/depth/normals/mask + loss D2H, sync"},
+        "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+        "host_launches_per_step": (1 if mode == "graph" else int(launches_per_step)),
+        "clocks": clocks.summary(), "roofline": roof,
+        "step_ms": {"resident": [round(x, 3) for x in t_res], "e2e": [round(x, 3) for x in t_e2e],
+                    "resident_stats": {k: round(v, 3) for k, v in st_res.items()}, "e2e_stats": {k: round(v, 3) for k, v in st_e2e.items()}},
     }
     if args.impl == "reference-cuda":
         line["impl"] = "reference-cuda"
         line["gpu_launches"] = 0
         line["config"]["note"] = "the reference's own CUDA kernels (oracle/_ref) under the same orchestration; no neuralsim_b200 kernel runs"
-    elif world == 1 and not args.no_ref_cuda:
-        # B1 of BASELINE.md, measured in a child process so that none of its module patching can leak into this arm
+    elif world == 1 and not args.no_ref_cuda and args.workload == "cfg2":
+        # B1 of BASELINE.md, measured in a child process so that none of its module patching can leak into this arm; it also dumps its
+        # eval render of view 0, against which ours is compared (BASELINE.json: "PSNR vs ref"; north_star: 1e-4 relative L2)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--steps", "2", "--warmup", "2",
-                                "--no-cpu-baseline", "--rayschunk", str(args.rayschunk), "--rays", str(args.rays)] + (["--random-rays"] if args.random_rays else [])
+            dump = f"/tmp/nsb_ref_render_{os.getpid()}.pt"
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--steps", "10", "--warmup", "3",
+                                "--no-cpu-baseline", "--rays", str(args.rays), "--dump-render", dump] + (["--random-rays"] if args.random_rays else [])
                                + (["--collect-samples"] if args.collect_samples else []),
-                               capture_output=True, text=True, timeout=600)
+                               capture_output=True, text=True, timeout=900)
             rl = json.loads(r.stdout.strip().splitlines()[-1])
-            line["reference_cuda"] = {"value": rl["value"], "unit": "Mrays/s", "ms_per_step": rl["ms_per_step"], "e2e": rl["e2e"]["value"],
+            line["reference_cuda"] = {"value": rl["value"], "unit": "Mrays/s", "ms_per_step": rl["ms_per_step"], "median_ms_per_step": rl["median"]["ms_per_step"],
+                                      "e2e": rl["e2e"]["value"], "steps": rl["steps"], "warmup": rl["warmup"],
                                       "what": "reference nr3d_lib CUDA kernels compiled from /root/reference (oracle/_ref), same B200, same workload"}
+            line["vs_reference_cuda"] = {"value_ratio": line["value"] / rl["value"], "e2e_ratio": line["e2e"]["value"] / rl["e2e"]["value"],
+                                         "median_ratio": line["median"]["value"] / rl["median"]["value"]}
+            if os.path.exists(dump):
+                ref = torch.load(dump)
+                with torch.no_grad():
+                    model.eval()
+                    o0, d0 = pinhole_rays(H, W, orbit(0, N_VIEWS))
+                    ours = SingleVolumeRenderer(dict(near=near)).eval().render(model, o0.to(device), d0.to(device), rays_h_appear=torch.zeros(o0.shape[0], n_appear, device=device))["rendered"]
+                    model.train()
+                par = {}
+                for kk in keys:
+                    x, y = ours[kk].double().cpu(), ref[kk].double()
+                    mse = float((x - y).square().mean())
+                    par[kk] = {"rel_l2": float((x - y).norm() / y.norm().clamp_min(1e-30)), "psnr_db": (None if mse == 0 else -10.0 * math.log10(mse))}
+                line["parity_vs_reference_kernels"] = {"what": "800x600 eval render of view 0, ours vs the reference's own kernels (same weights, rays, grid); "
+                                                               "psnr_db null = identical", **par}
+                os.remove(dump)
         except Exception as ex:
-            line["reference_cuda"] = {"unavailable": repr(ex)[:200]}
+            line["reference_cuda"] = {"unavailable": repr(ex)[:300]}
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(args.ref_rays)

@@ -147,14 +147,14 @@ class _FusedSDF(autograd.Function):
             sdf = owner._launch_sdf(grid16, dec, pts, max_level)
         n = sdf.shape[0]
         ctx.owner, ctx.pts, ctx.max_level, ctx.n = owner, pts[:5] if isinstance(pts, tuple) else pts, max_level, n
-        ctx.held = (grid16, dec)          # the fp16 images the forward used
+        ctx.held = (grid16, dec, owner._fused_cache[1])          # the fp16 images the forward used (the tensors `dec` points into stay alive)
         ctx.shapes = (grid.shape, W1.shape, b1.shape, W2.shape, b2.shape)
         return sdf
 
     @staticmethod
     @autograd.function.once_differentiable
     def backward(ctx, d_sdf):
-        grid16, dec = ctx.held
+        grid16, dec, _alive = ctx.held
         meta, dev = ctx.owner.encoding.meta, d_sdf.device
         gs, w1s, b1s, w2s, b2s = ctx.shapes
         d_grid = torch.zeros(gs, dtype=torch.float32, device=dev)
@@ -287,9 +287,14 @@ class LoTDSDF(nn.Module):
 
     # ---- fused no-grad query (csrc/fused.cu)
     def _fusable(self):
+        """the preconditions of the fused kernels (csrc/fused_tc.cu: `n_pseudo == 16 && F == 2 && plmeta_two_feature_cells`, width <= 64, both
+        biases, CUDA parameters); any other valid LoTD / decoder configuration takes the generic encoding -> decoder path of forward()"""
         e, d = self.encoding, self.decoder
+        m = e.meta
         return (self.dtype == torch.half and e.window is None and d.D == 1 and e.out_features == 32 and e.in_features == 3
-                and d.layers[0].out_features <= 64 and isinstance(d.layers[0].activation, nn.Softplus) and d.layers[1].bias is not None)
+                and m.n_pseudo_levels == 16 and m.n_feat_per_pseudo_lvl == 2 and all(f == 2 for f in m.level_n_feats)
+                and d.layers[0].out_features <= 64 and isinstance(d.layers[0].activation, nn.Softplus)
+                and d.layers[0].bias is not None and d.layers[1].bias is not None and e.flattened_params.is_cuda)
 
     def _fused_state(self):
         """fp16 images of the masters, rebuilt when any master changed (version counters)."""

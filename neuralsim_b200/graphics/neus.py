@@ -159,7 +159,9 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, perturb=False, 
 def _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths, *, nablas_has_grad,
                       with_rgb, with_normal, dtype):
     if (FUSED_STAGES and with_rgb and view_dirs is not None and getattr(model, "_color_fusable", lambda: False)()
-            and not (rays_h_appear is not None and rays_h_appear.requires_grad) and not depths.requires_grad):
+            and not (rays_h_appear is not None and rays_h_appear.requires_grad) and not depths.requires_grad
+            # learnable rays (pose refinement): the reference's model.forward(x = o + d t) carries d(loss)/d(rays); the fused op detaches them
+            and not (rays_o.requires_grad or rays_d.requires_grad or view_dirs.requires_grad)):
         out = model.forward_on_rays(ridx_all, depths, rays_o, rays_d, view_dirs, rays_h_appear, nablas_has_grad=nablas_has_grad)
         volume_buffer["net_x"] = out["x"]
         volume_buffer["nablas"] = out["nablas"].to(dtype)
