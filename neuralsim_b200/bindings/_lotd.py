@@ -169,3 +169,8 @@ def lod_bwd_bwd_input(lod_meta, dL_ddLdx, dL_dy, input, params, dy_dx=None, batc
         L.c_i64(n), L.c_i32(ml), L.c_f32(1.0), L.ptr(out_y, allow_none=True), L.ptr(acc, allow_none=True),
         L.stream_ptr()), "lod_bwd_bwd_input")
     return (None if out_y is None else out_y.to(dL_dy.dtype)), (None if acc is None else acc.to(params.dtype)), None
+
+
+def lod_get_grid_index(*a, **k):
+    """lotd.cpp: debugging helper that returns the table indices of the corners; not on any training / rendering path"""
+    raise RuntimeError("_lotd.lod_get_grid_index is not built in neuralsim_b200 (debug helper outside the hot path)")

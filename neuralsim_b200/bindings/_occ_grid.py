@@ -71,3 +71,8 @@ def batched_ray_marching(rays_o, rays_d, t_min, t_max, batch_inds, batch_data_si
                                             batch_inds.contiguous().int(), type, step_size, max_step_size, dt_gamma, max_steps,
                                             return_gidx, "batched_ray_marching")
     return [info, t0, t1, ridx, bidx, gidx]
+
+
+def forest_ray_marching(*a, **k):
+    """occ_grid.cpp:21-33 `forest_ray_marching(ForestMeta, ...)`: needs the forest block space (`_forest`, kaolin) -- not built"""
+    raise RuntimeError("_occ_grid.forest_ray_marching is not built in neuralsim_b200 (forest block spaces, SURVEY.md §8 a13)")

@@ -214,3 +214,23 @@ def mark_pack_boundaries_cuda(ids):
     out = torch.empty(ids.shape[0], dtype=torch.int32, device=ids.device)
     L.check(L.lib().nsb_mark_pack_boundaries(L.ptr(ids), L.c_i64(ids.shape[0]), L.ptr(out), L.stream_ptr()), "mark_pack_boundaries")
     return out
+
+
+def packed_sort_thrust(vals, pack_infos, return_idx=True):
+    """pack_ops.cpp: the thrust variant of the per-pack sort (commented out at its only call site, pack_ops.py:75): same contract as the qsort entry"""
+    return packed_sort_qsort(vals, pack_infos, return_idx)
+
+
+def _not_built(name, where):
+    def fn(*a, **k):
+        raise RuntimeError(f"_pack_ops.{name} is not built in neuralsim_b200: {where}")
+    fn.__name__ = name
+    return fn
+
+
+# producers / searches no shipped NeuS query mode reaches (their callers: AABBSpace.ray_step_coarse `wrt_depth` modes, aabb.py:128;
+# ForestBlockSpace, forest.py:407; octree segments): named so that a call fails with a message instead of an AttributeError
+interleave_sample_step_wrt_depth_clamped = _not_built("interleave_sample_step_wrt_depth_clamped", "depth-proportional coarse stepping (CFG uses step_mode 'linear')")
+interleave_sample_step_wrt_depth_in_packed_segments = _not_built("interleave_sample_step_wrt_depth_in_packed_segments", "forest block segments")
+packed_searchsorted_packed_vals = _not_built("packed_searchsorted_packed_vals", "ragged search values (no caller on the NeuS path)")
+octree_mark_consecutive_segments = _not_built("octree_mark_consecutive_segments", "octree (forest) ray segments")
