@@ -325,6 +325,17 @@ int nsb_ray_test_aabb(const float *rays_o, const float *rays_d, int64_t n, const
 int nsb_gather_rays(const int64_t *idx, int64_t n, const float *o_n, const float *d_n, const float *near, const float *far, float *o_c,
                     float *d_c, float *near_c, float *far_c, const float *extra, float *extra_c, int32_t extra_cols, void *stream);
 
+/* ---------------------------------------------------------------- occupancy-grid maintenance (csrc/occ_ema.cu)
+ * OccGridEma._step_update_occ (nr3d_lib/models/accelerations/occgrid/ema_single.py:176-190; occgrid/utils.py:63-101) in three small launches:
+ * evidence of n points (val = sdf -> normalized_logistic_density on fp16, or val = ready evidence) max-scattered into their voxels
+ * ((pts/2+0.5) res, clamped), merged with the non-zero cells of the collected-evidence grid `pcl` (zeroed afterwards; may be NULL), then
+ * on every TOUCHED voxel  grid = max(ema_decay grid, evidence);  occ_grid = grid > occ_thre on all voxels; occ_bits (may be NULL) = the
+ * bool grid packed 32 cells / word (what nsb_ray_marching_listed takes).  scratch_cells: rx ry rz floats.  Replaces torch_scatter's
+ * scatter_max + index_put + nonzero (a host sync) of the reference. */
+int nsb_occ_ema_update(const float *pts, const float *val, int64_t n, int32_t val_is_sdf, float inv_s, int32_t rx, int32_t ry, int32_t rz,
+                       float *pcl_or_null, float *occ_val_grid, uint8_t *occ_grid, uint32_t *occ_bits_or_null, float ema_decay, float occ_thre,
+                       float *scratch_cells, void *stream);
+
 /* ---------------------------------------------------------------- fused colour / normal query (csrc/color_tc.cu)
  * The whole LoTDNeuS.forward of the reference for packed samples (nr3d_lib/models/fields/neus/lotd_neus.py:141-167 =
  * LoTDSDF.forward_sdf_nablas, lotd_sdf.py:201-257, + RadianceNet.forward, mlp_nerf.py:267-289) as one tcgen05 kernel, and

@@ -11,6 +11,11 @@ import torch.nn as nn
 from ..graphics.raymarch import occgrid_raymarch
 
 
+# True: the EMA update of a CUDA grid runs as the kernels of csrc/occ_ema.cu; False: as the torch restatement of the reference's chain
+# (scatter_reduce_('amax') for torch_scatter's scatter_max) -- tests/test_occ_ema_gpu.py compares both with the oracle.
+DEVICE_EMA = True
+
+
 def sample_pts_in_voxels(gidx, num_pts, resolution, dtype=torch.float, generator=None):
     """Uniform points in [-1,1]^3 inside the listed voxels (+ the voxel each one fell in)  (utils.py:17-41)."""
     device, nv = gidx.device, gidx.shape[0]
@@ -83,6 +88,26 @@ class OccGridEma(nn.Module):
         self.occ_grid = self.occ_val_grid > self.occ_thre
 
     @torch.no_grad()
+    def _step_update_device(self, pts, sdf):
+        """`_step_update_occ` (ema_single.py:176-190) as the three launches of csrc/occ_ema.cu: evidence of the points (from their sdf) and the
+        evidence collected while rendering -> decay + max on the touched voxels -> threshold (+ the bit-packed grid the marcher reads).
+        No nonzero(), no host read."""
+        from .. import _lib as L
+        r = [int(v) for v in self.occ_val_grid.shape]
+        pts = pts.detach().reshape(-1, 3).contiguous().float()
+        sdf = sdf.detach().reshape(-1).contiguous().float()
+        pcl = self._occ_val_grid_pcl if self.should_collect_samples else None
+        scratch = torch.empty(self.occ_val_grid.numel(), dtype=torch.float32, device=pts.device)
+        occ = torch.empty(r, dtype=torch.bool, device=pts.device)
+        grid = self.occ_val_grid if (self.occ_val_grid.is_contiguous() and self.occ_val_grid.dtype == torch.float32) else self.occ_val_grid.contiguous().float()
+        L.check(L.lib().nsb_occ_ema_update(L.ptr(pts, "f32"), L.ptr(sdf, "f32"), L.c_i64(pts.shape[0]), L.c_i32(1), L.c_f32(self.occ_inv_s), L.c_i32(r[0]),
+                                           L.c_i32(r[1]), L.c_i32(r[2]), L.ptr(pcl, "f32", allow_none=True), L.ptr(grid, "f32"), L.ptr(occ.view(torch.uint8), "u8"),
+                                           None, L.c_f32(self.ema_decay), L.c_f32(self.occ_thre), L.ptr(scratch), L.stream_ptr()), "occ_ema_update")
+        if grid is not self.occ_val_grid:
+            self.occ_val_grid.copy_(grid)
+        self.occ_grid = occ
+
+    @torch.no_grad()
     def set_occ_grid(self, occ_grid):
         self.occ_grid = occ_grid.to(self.occ_grid.device).bool().contiguous()
         self.occ_val_grid = self.occ_grid.to(self.occ_val_grid.dtype)
@@ -129,6 +154,9 @@ class OccGridEma(nn.Module):
                 pts = torch.cat(parts, 0)
             pts_all.append(pts)
             val_all.append(val_query_fn(pts))
+        if DEVICE_EMA and self.occ_val_grid.is_cuda and self.occ_val_grid.dim() == 3:
+            self._step_update_device(torch.cat(pts_all, 0), torch.cat(val_all, 0))
+            return True
         pts, occ_val = torch.cat(pts_all, 0), self.occ_val_fn(torch.cat(val_all, 0).flatten())
         gidx = self._gidx_of(pts)
         if self.should_collect_samples:
