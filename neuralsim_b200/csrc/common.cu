@@ -1,6 +1,10 @@
 // Error channel, version and launch counter of the neuralsim_b200 C ABI.
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "nsb_common.cuh"
 
 namespace nsb {
@@ -23,6 +27,18 @@ DevCounts take_counts() {
     const DevCounts c = g_counts;
     g_counts = DevCounts{nullptr, nullptr};
     return c;
+}
+}  // namespace nsb
+
+namespace nsb {
+bool smem_opt_in_needed(const void *kernel, int dev, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> granted;
+    std::lock_guard<std::mutex> lock(mu);
+    int &g = granted[std::make_pair(kernel, dev)];
+    if (g >= bytes) return false;
+    g = bytes;
+    return true;
 }
 }  // namespace nsb
 

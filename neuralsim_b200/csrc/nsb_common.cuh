@@ -54,13 +54,12 @@ inline int sm_count() {
 }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and the call is not free
+bool smem_opt_in_needed(const void *kernel, int dev, int bytes);       // common.cu: remembers (kernel, device) -> bytes already granted
 template <typename K>
 inline void opt_in_smem(K kernel, int bytes) {
-    static std::atomic<int> done[64];
-    const int dev = current_device() & 63;
-    if (done[dev].load(std::memory_order_relaxed) >= bytes) return;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    done[dev].store(bytes, std::memory_order_relaxed);
+    // keyed by the kernel's ADDRESS: two instantiations of one template share their function-pointer type
+    if (smem_opt_in_needed(reinterpret_cast<const void *>(kernel), current_device(), bytes))
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 // Device-resident counts (nsb_bind_device_counts, include/neuralsim_b200.h): the entry points that support them take the binding of the

@@ -186,6 +186,10 @@ class OccGridAccel(nn.Module):
     def __init__(self, space=None, device=None, **occ_cfg):
         super().__init__()
         occ_cfg.pop("type", None)
+        vox_size = occ_cfg.pop("vox_size", None)
+        if vox_size is not None and "resolution" not in occ_cfg:
+            # occgrid_accel/single.py:51-55: a voxel edge in world units -> per-axis resolution of the cuboid space
+            occ_cfg["resolution"] = [max(int(float(e) / float(vox_size)), 1) for e in (space.radius3d * 2).tolist()]      # `.long()`: truncation
         self.space = space
         self.occ = OccGridEma(**occ_cfg, device=device)
         self.training_granularity = 0.0

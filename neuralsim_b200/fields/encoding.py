@@ -24,6 +24,27 @@ def gen_ngp_cfg(min_res=16, dim=3, n_feats=2, log2_hashmap_size=19, per_level_sc
     return dict(lod_res=res.tolist(), lod_n_feats=[n_feats] * num_levels, lod_types=types, hashmap_size=hashmap_size)
 
 
+def auto_ngp_cfg(stretch, target_num_params, *, dim=3, n_feats=2, log2_hashmap_size=19, min_res=4, per_level_scale=1.382, max_num_levels=128):
+    """The [Dense -> Hash] ladder the reference computes for cuboid spaces (`lotd_auto_compute_cfg: {type: ngp}`, lotd_cfg.py:59-133): the last
+    dense level holds ~ hashmap/2.5 cells with the aspect ratio of `stretch`, the dense levels shrink from it by per_level_scale down to
+    ~min_res on the shortest side, the hashed levels grow from it; their number follows from target_num_params."""
+    stretch = np.array([stretch] * dim if np.isscalar(stretch) else list(stretch), dtype=np.float64)
+    hashmap_size = 2 ** log2_hashmap_size
+    dense_factor = (stretch / stretch.min()).prod()
+    dense_last_min_res = int((hashmap_size / 2.5 / dense_factor) ** (1 / 3))
+    num_dense = max(int(np.exp(np.log(dense_last_min_res / min_res) / per_level_scale) + 1), 1)
+    num_hash = max(int(target_num_params / (hashmap_size * n_feats) - 1 + 0.5), 0)
+    num_levels = num_dense + num_hash
+    if max_num_levels is not None:
+        num_levels = min(num_levels, max_num_levels)
+        num_hash = num_levels - num_dense
+    last = stretch / (stretch.min() / dense_last_min_res)
+    res_dense = (last[..., None] / (per_level_scale ** np.arange(num_dense)))[:, ::-1].T.astype(int)
+    res_hash = (last[..., None] * (per_level_scale ** (np.arange(num_hash) + 1))).T.astype(int)
+    res = np.concatenate([res_dense, res_hash], axis=0)
+    return dict(lod_res=res.tolist(), lod_n_feats=[n_feats] * num_levels, lod_types=["Dense"] * num_dense + ["Hash"] * num_hash, hashmap_size=hashmap_size)
+
+
 def generate_meta(n_input_dim, lod_res, lod_n_feats, lod_types, hashmap_size=None, use_smooth_step=False):
     if isinstance(lod_n_feats, int):
         lod_n_feats = [lod_n_feats] * len(lod_res)
@@ -163,14 +184,24 @@ class LoTDEncoding(nn.Module):
     (lotd_encoding.py:37-213; state-dict key `...encoding.flattened_params`)."""
 
     def __init__(self, input_ch=3, *, lotd_cfg: dict = None, lotd_auto_compute_cfg: dict = None, param_init_cfg=dict(type="uniform_to_type", bound=1.0e-4),
-                 dtype=torch.half, device=None, generator=None):
+                 dtype=torch.half, device=None, generator=None, lotd_use_cuboid=False, aabb=None):
         super().__init__()
         if lotd_cfg is None:
             auto = dict(lotd_auto_compute_cfg or dict(type="gen_ngp"))
             kind = auto.pop("type", "gen_ngp")
-            if kind != "gen_ngp":
-                raise RuntimeError(f"lotd_auto_compute_cfg type={kind!r} is not built (gen_ngp only)")
-            lotd_cfg = gen_ngp_cfg(dim=input_ch, **auto)
+            if kind == "gen_ngp":
+                lotd_cfg = gen_ngp_cfg(dim=input_ch, **auto)
+            elif kind == "ngp":
+                # lotd_encoding.py:60-75: cuboid spaces stretch the level resolutions with the aabb's aspect ratio
+                stretch = 1.0
+                if lotd_use_cuboid:
+                    if aabb is None:
+                        raise RuntimeError("lotd_use_cuboid needs the aabb of the space")
+                    ab = torch.as_tensor(aabb, dtype=torch.float64)
+                    stretch = (ab[1] - ab[0]).tolist()
+                lotd_cfg = auto_ngp_cfg(stretch, dim=input_ch, **auto)
+            else:
+                raise RuntimeError(f"lotd_auto_compute_cfg type={kind!r} is not built (gen_ngp, ngp)")
         self.lotd_cfg = lotd_cfg
         self.lotd = LoTD(input_ch, **lotd_cfg, dtype=dtype, device=device)
         self.dtype = dtype

@@ -193,16 +193,17 @@ class LoTDSDF(nn.Module):
     """LoTD encoding + MLP decoder -> sdf (and nablas by analytic back-propagation through decoder and table)."""
 
     def __init__(self, encoding_cfg: dict = None, decoder_cfg: dict = None, dtype=torch.half, device=None, generator=None,
-                 sdf_scale=1.0, radius3d_original=1.0):
+                 sdf_scale=1.0, radius3d_original=1.0, aabb=None):
         super().__init__()
         self.dtype = dtype
-        self.encoding = LoTDEncoding(3, **(encoding_cfg or {}), dtype=dtype, device=device, generator=generator)
+        self.encoding = LoTDEncoding(3, **(encoding_cfg or {}), dtype=dtype, device=device, generator=generator, aabb=aabb)
         dc = dict(D=1, W=64, activation=dict(type="softplus", beta=100.0))
         dc.update(decoder_cfg or {})
         dc.pop("type", None)
         self.decoder = MLP(self.encoding.out_features, 1, **dc, dtype=dtype, device=device, generator=generator)
         self.sdf_scale = sdf_scale
-        self.register_buffer("radius3d_original", torch.full([3], float(radius3d_original), device=device), persistent=True)
+        r3 = torch.as_tensor(radius3d_original, dtype=torch.float, device=device)
+        self.register_buffer("radius3d_original", r3.expand(3).clone() if r3.numel() == 1 else r3.reshape(3).clone(), persistent=True)
         self.register_buffer("is_pretrained", torch.tensor([False], dtype=torch.bool, device=device), persistent=True)
         self._fused_cache = None
 

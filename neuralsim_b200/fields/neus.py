@@ -36,9 +36,11 @@ class LoTDNeuS(nn.Module):
         self.dtype = dtype
         sc = dict(surface_cfg or {})
         bounding_size = sc.pop("bounding_size", 2.0)
-        self.space = AABBSpace(bounding_size, device=device)
+        aabb = sc.pop("aabb", None)                      # a cuboid space (street scenes: LoTDNeuSStreet, `lotd_use_cuboid`)
+        self.space = AABBSpace(bounding_size, aabb=aabb, device=device)
         self.implicit_surface = LoTDSDF(encoding_cfg=sc.get("encoding_cfg"), decoder_cfg=sc.get("decoder_cfg"), dtype=dtype, device=device,
-                                        generator=generator, radius3d_original=bounding_size / 2.)
+                                        generator=generator, sdf_scale=sc.get("sdf_scale", 1.0), aabb=self.space.aabb.cpu(),
+                                        radius3d_original=(self.space.radius3d_original.cpu() if aabb is not None else bounding_size / 2.))
         rc = dict(use_pos=True, use_view_dirs=True, use_nablas=True, D=2, W=64)
         rc.update(radiance_cfg or {})
         if n_appear_embedding is not None:

@@ -289,10 +289,10 @@ def static_supported(model, cfg):
     occ = getattr(getattr(model, "accel", None), "occ", None)
     return (getattr(model, "_color_fusable", lambda: False)() and model.use_view_dirs and occ is not None and occ.occ_grid.dim() == 3
             and occ.occ_grid.numel() * 4 // 32 <= 96 * 1024 and qp.get("num_coarse", 0) > 0 and len(qp.get("upsample_inv_s_factors", (1, 4, 16))) <= 4
-            and qp.get("coarse_step_cfg", {}).get("step_mode", "linear") == "linear" and cfg.get("with_rgb", True))
+            and qp.get("coarse_step_cfg", {}).get("step_mode", "linear") == "linear" and (cfg.get("with_rgb", True) or cfg.get("with_normal", True)))
 
 
-def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=None, march_cap, kept_cap, coherent=False, with_normal=True,
+def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=None, march_cap, kept_cap, coherent=False, with_rgb=True, with_normal=True,
                   perturb=False, training=None, depth_use_normalized_vw=True, cnt=None):
     """One chunk of rays, ray test -> query -> integration, without a host read.  -> (rendered dict of whole-chunk images, cnt int64[32]).
     `coherent`: image-ordered rays (the boundary / fine queries then walk the samples ray-tiled) -- a host decision here (the host-sized
@@ -349,6 +349,8 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
         o_c, d_c = torch.zeros(R, 3, device=dev), torch.zeros(R, 3, device=dev)
         n_c, f_c = torch.zeros(R, device=dev), torch.zeros(R, device=dev)
         ha = rays_h_appear.detach().contiguous().float() if (rays_h_appear is not None and model.use_h_appear) else None
+        if ha is None and model.use_h_appear:             # LiDAR-style rays carry no appearance code: the (dropped) radiance head reads zeros
+            ha = torch.zeros(R, model.radiance_net.blocks.layers[0].in_features - 54, device=dev)
         ha_c = torch.zeros(R, ha.shape[1], device=dev) if ha is not None else None
         _call(lib.nsb_gather_rays, "gather_rays", cnt, CNT_SLOTS["n_rays"], None, P(rays_inds, "i64"), L.c_i64(R), P(o_n), P(d_n), P(nr), P(fr), P(o_c), P(d_c),
               P(n_c), P(f_c), P(ha, allow_none=True), P(ha_c, allow_none=True), L.c_i32(0 if ha is None else ha.shape[1]), L.stream_ptr())
@@ -449,8 +451,11 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
     nab_i = nab if with_normal else None
     if nab_i is not None and not training:
         nab_i = F.normalize(nab_i.clamp(-1, 1), dim=-1)
-    vw, m, d, c, nn_ = _StaticComposite.apply(alpha_k, t_k, rgb, nab_i, pinfo_kept, rays_inds_hit, R, cnt, bool(depth_use_normalized_vw), 1e-4, 0.0)
-    rendered = dict(mask_volume=m, depth_volume=d, rgb_volume=c)
+    vw, m, d, c, nn_ = _StaticComposite.apply(alpha_k, t_k, rgb if with_rgb else None, nab_i, pinfo_kept, rays_inds_hit, R, cnt,
+                                              bool(depth_use_normalized_vw), 1e-4, 0.0)
+    rendered = dict(mask_volume=m, depth_volume=d)
+    if with_rgb:
+        rendered["rgb_volume"] = c
     if with_normal:
         rendered["normals_volume"] = nn_
     buffers = dict(opacity_alpha=alpha_k, t=t_k, rgb=rgb, nablas=nab, net_x=x, vw=vw, pack_infos_hit=pinfo_kept, rays_inds_hit=rays_inds_hit, ridx=ridx_k,
@@ -485,10 +490,10 @@ class StaticFrame:
     The first call probes the sizes with the host-sized path (SingleVolumeRenderer.ray_query, no grad), sizes the arenas with `slack`,
     warms up and captures.  Gradients are accumulated into `p.grad` (kept in place; `zero_grads=True` zeroes them inside the graph)."""
 
-    def __init__(self, model, n_rays, loss_fn=None, *, near=None, far=None, with_normal=True, slack=1.5, march_cap=None, kept_cap=None, coherent=None,
-                 use_graph=True, zero_grads=False, h_appear_dim=None, pre_hook=None):
+    def __init__(self, model, n_rays, loss_fn=None, *, near=None, far=None, with_rgb=True, with_normal=True, slack=1.5, march_cap=None, kept_cap=None,
+                 coherent=None, use_graph=True, zero_grads=False, h_appear_dim=None, pre_hook=None):
         self.model, self.n_rays, self.loss_fn = model, int(n_rays), loss_fn
-        self.near, self.far, self.with_normal, self.slack = near, far, with_normal, float(slack)
+        self.near, self.far, self.with_rgb, self.with_normal, self.slack = near, far, with_rgb, with_normal, float(slack)
         self.march_cap, self.kept_cap, self.coherent = march_cap, kept_cap, coherent
         self.use_graph, self.zero_grads, self.pre_hook = use_graph, zero_grads, pre_hook
         dev = model.device
@@ -506,7 +511,7 @@ class StaticFrame:
     def _probe(self):
         """sizes of this batch from the host-sized path (two host reads): M (merged marched samples), K (kept), coherence"""
         from ..renderer import SingleVolumeRenderer
-        r = SingleVolumeRenderer(dict(near=self.near, far=self.far, with_normal=self.with_normal))
+        r = SingleVolumeRenderer(dict(near=self.near, far=self.far, with_rgb=self.with_rgb, with_normal=self.with_normal))
         r.train(self.model.training)
         out = r.ray_query(self.model, self.rays_o, self.rays_d, self.h_appear, return_buffer=True, return_details=True)
         det, vb = out.get("details", {}), out["volume_buffer"]
@@ -538,7 +543,7 @@ class StaticFrame:
                 if p.grad is not None:
                     p.grad.zero_()
         rendered, _, buffers = render_static(self.model, self.rays_o, self.rays_d, self.h_appear, near=self.near, far=self.far, march_cap=self.march_cap,
-                                             kept_cap=self.kept_cap, coherent=bool(self.coherent), with_normal=self.with_normal, cnt=self.cnt)
+                                             kept_cap=self.kept_cap, coherent=bool(self.coherent), with_rgb=self.with_rgb, with_normal=self.with_normal, cnt=self.cnt)
         loss = None
         if self.loss_fn is not None:
             loss = self.loss_fn(rendered)
@@ -564,7 +569,10 @@ class StaticFrame:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # capture on the warm-up's stream: the parameters' AccumulateGrad nodes were created there.  (A backward that ran on the default
+            # stream BEFORE this and whose graph is still referenced -- a kept loss / rendered tensor -- pins those nodes to the default
+            # stream and invalidates the capture: drop such references first.)
+            with torch.cuda.graph(g, stream=side):
                 self.rendered, self.buffers, self.loss = self._run()
             self.graph = g
             self.captures += 1

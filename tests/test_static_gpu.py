@@ -75,7 +75,8 @@ def test_graph_replay_equals_host_sized_step(cuda):
     for k in views:
         ro, rd = _rays(cuda, k=k)
         out, g = _host_sized(model, ro, rd, ha)
-        refs.append(({kk: out["rendered"][kk].clone() for kk in KEYS}, g))
+        refs.append(({kk: out["rendered"][kk].detach().clone() for kk in KEYS}, g))
+        del out                                          # drop the autograd graph: its AccumulateGrad nodes live on the default stream
     for p in model.parameters():
         p.grad = torch.zeros_like(p)                     # the buffers the graph accumulates into
     frame = StaticFrame(model, n, loss_fn=_loss, near=0.01, zero_grads=True, slack=2.0)
