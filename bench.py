@@ -243,6 +243,141 @@ def use_reference_cuda_kernels():
     return True
 
 
+# ---------------------------------------------------------------------------------------------- cfg3 arm
+def run_cfg3(args, rank, world, local, device):
+    """BASELINE.json configs[2] (bench_cfg3.py): per step 8192 camera rays (rgb + normals) and 8192 LiDAR rays (depth + normals) through the
+    street-segment model, fwd + bwd; each ray kind is one CUDA-graph launch (graph mode) or the host-sized path (host mode)."""
+    import torch.distributed as dist
+    import bench_cfg3 as C
+    from neuralsim_b200 import _lib
+    from neuralsim_b200.renderer import SingleVolumeRenderer
+    from neuralsim_b200.graphics.neus_static import StaticFrame
+    mode = "host" if args.impl == "reference-cuda" else args.mode
+    if args.impl == "reference-cuda" and not use_reference_cuda_kernels():
+        raise SystemExit("bench.py: oracle/_ref is not built")
+    model = C.build_model(device).train()
+    flat, params = flat_grad_views(model)
+    views_dev, views_host = [], []
+    for k in range(N_VIEWS):
+        (co, cd), (lo, ld) = C.make_views(k, rank, world)
+        views_host.append(tuple(t.pin_memory() for t in (co, cd, lo, ld)))
+        views_dev.append(tuple(t.to(device) for t in (co, cd, lo, ld)))
+    n_rays = C.N_CAM + C.N_LIDAR
+    ha = torch.zeros(C.N_CAM, 4, device=device)
+    r_cam = SingleVolumeRenderer(dict(near=C.NEAR, far=C.FAR)).train()
+    r_lidar = SingleVolumeRenderer(dict(near=C.NEAR, far=C.FAR, with_rgb=False, with_normal=True)).train()
+    f_cam = f_lidar = None
+    launches_per_step = None
+    if mode != "host":
+        f_cam = StaticFrame(model, C.N_CAM, loss_fn=C.loss_cam, near=C.NEAR, far=C.FAR, use_graph=(mode == "graph"), pre_hook=flat.zero_, slack=2.0)
+        f_lidar = StaticFrame(model, C.N_LIDAR, loss_fn=C.loss_lidar, near=C.NEAR, far=C.FAR, with_rgb=False, use_graph=(mode == "graph"), slack=2.0)
+        for k in range(N_VIEWS):
+            f_cam.rays_o.copy_(views_dev[k][0]); f_cam.rays_d.copy_(views_dev[k][1]); f_cam._size()
+            f_lidar.rays_o.copy_(views_dev[k][2]); f_lidar.rays_d.copy_(views_dev[k][3]); f_lidar._size()
+        l0 = _lib.launch_count()
+        f_cam.capture(); f_lidar.capture()
+        launches_per_step = (_lib.launch_count() - l0) // (3 if mode == "graph" else 1) if mode == "graph" else None      # 2 warm-up runs + the captured one
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    loss_host = torch.zeros((), pin_memory=True)
+    out_host = {"rgb": torch.zeros(C.N_CAM, 3).pin_memory(), "depth_cam": torch.zeros(C.N_CAM).pin_memory(), "depth_lidar": torch.zeros(C.N_LIDAR).pin_memory()}
+    last = {}
+
+    def step(v):
+        co, cd, lo, ld = v
+        if f_cam is not None:
+            l1 = f_cam.step(co, cd, None)
+            l2 = f_lidar.step(lo, ld, None)
+            last["cam"], last["lidar"] = f_cam.rendered, f_lidar.rendered
+            loss = l1 + l2
+        else:
+            flat.zero_()
+            co, cd, lo, ld = (t.to(device, non_blocking=True) for t in v)
+            a = r_cam.render(model, co, cd, rays_h_appear=ha)["rendered"]
+            b = r_lidar.render(model, lo, ld)["rendered"]
+            loss = C.loss_cam(a) + C.loss_lidar(b)
+            if loss.requires_grad:
+                loss.backward()
+            last["cam"], last["lidar"] = a, b
+            loss = loss.detach()
+        if world > 1:
+            dist.all_reduce(flat)
+        return loss
+
+    def timed(fn, k, sampler=None):
+        evs = []
+        for i in range(k):
+            flush_buf.fill_(i & 0xff)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(i); b.record()
+            evs.append((a, b))
+        if sampler is not None:
+            sampler.sample()
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    n_views = max(1, min(N_VIEWS, args.warmup))
+
+    def resident(i):
+        return step(views_dev[i % n_views])
+
+    def e2e(i):
+        loss = step(views_host[i % n_views])
+        out_host["rgb"].copy_(last["cam"]["rgb_volume"], non_blocking=True)
+        out_host["depth_cam"].copy_(last["cam"]["depth_volume"], non_blocking=True)
+        out_host["depth_lidar"].copy_(last["lidar"]["depth_volume"], non_blocking=True)
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    with ClockSampler(local, args.clock_period_ms) as clocks:
+        for i in range(args.warmup):
+            resident(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_e2e = timed(e2e, args.steps)
+        if world > 1:
+            dist.barrier()
+        t_res = timed(resident, args.steps, clocks)
+    st_res, st_e2e = stats_of(t_res), stats_of(t_e2e)
+    ms = torch.tensor([st_res["mean"], st_e2e["mean"], st_res["median"], st_e2e["median"]], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+    ms_res, ms_e2e, med_res, med_e2e = (float(x) for x in ms)
+    tot = world * n_rays
+    meta = model.implicit_surface.encoding.meta
+    counts = {"cam": f_cam.counts(), "lidar": f_lidar.counts()} if f_cam is not None else None
+    line = {"metric": "Mrays/sec fwd+bwd", "value": tot / (ms_res * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "median": {"ms_per_step": med_res, "value": tot / (med_res * 1e-3) / 1e6, "e2e_ms_per_step": med_e2e, "e2e_value": tot / (med_e2e * 1e-3) / 1e6},
+            "config": {"workload": "cfg3", "what": "StreetSurf close-range model: cuboid aabb 40x150x15 m, cuboid LoTD (ngp auto config, 2^20 hash, max_num_levels 16 -- "
+                       "the shipped config's 17 levels run op by op), 1 m occupancy voxels, step 0.2, 128 coarse + [8,8,32] fine; 8192 camera rays (rgb+normals) + "
+                       "8192 LiDAR rays (with_rgb=False) per step", "lotd_levels": meta.n_levels, "lotd_params": int(meta.n_params),
+                       "lotd_res": [list(r) for r in meta.level_res_multidim], "occ_grid": list(model.accel.occ.occ_grid.shape), "mode": mode,
+                       "rays_per_step_per_gpu": n_rays, "parallelism": f"dp{world}", "l2": "256 MiB L2 flush between steps", "counts": counts},
+            "e2e": {"value": tot / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(2 * n_rays * 3 * 4),
+                    "d2h_bytes_per_step": int(sum(v.numel() * 4 for v in out_host.values()) + 4)},
+            "gpu_launches": (int(launches_per_step * args.steps) if launches_per_step else None), "launches_per_step": launches_per_step,
+            "host_launches_per_step": (2 if mode == "graph" else None), "clocks": clocks.summary(),
+            "step_ms": {"resident": [round(x, 3) for x in t_res], "e2e": [round(x, 3) for x in t_e2e]}}
+    if args.impl == "reference-cuda":
+        line["impl"] = "reference-cuda"
+    elif world == 1 and not args.no_ref_cuda:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--workload", "cfg3", "--steps", "10", "--warmup", "3"],
+                               capture_output=True, text=True, timeout=900)
+            rl = json.loads(r.stdout.strip().splitlines()[-1])
+            line["reference_cuda"] = {"value": rl["value"], "ms_per_step": rl["ms_per_step"], "e2e": rl["e2e"]["value"], "steps": rl["steps"]}
+            line["vs_reference_cuda"] = {"value_ratio": line["value"] / rl["value"], "e2e_ratio": line["e2e"]["value"] / rl["e2e"]["value"]}
+        except Exception as ex:
+            line["reference_cuda"] = {"unavailable": repr(ex)[:300]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------- main arm
 def stats_of(ts):
     a = np.asarray(ts, dtype=np.float64)
@@ -296,13 +431,10 @@ def main():
             raise SystemExit("bench.py: oracle/_ref is not built (python oracle/build_ref.py in the build container)")
         mode = "host"
     if args.workload == "cfg3":
-        import bench_cfg3
-        model = bench_cfg3.build_model(device).train()
-        make_views, near = bench_cfg3.make_views, bench_cfg3.NEAR
-        with_rgb_note = "8192 camera + 8192 LiDAR-like rays per step"
-    else:
-        model = build_model(device, collect_samples=args.collect_samples).train()
-        make_views, near = None, 0.01
+        run_cfg3(args, rank, world, local, device)
+        return
+    model = build_model(device, collect_samples=args.collect_samples).train()
+    near = 0.01
     renderer = SingleVolumeRenderer(dict(near=near, rayschunk=0)).train()
     flat, params = flat_grad_views(model)
     n_rays = args.rays
@@ -310,9 +442,7 @@ def main():
         n_rays = (args.rays + world - 1) // world
     views_host, views_dev = [], []
     for k in range(N_VIEWS):
-        if make_views is not None:
-            o, d = make_views(k, n_rays, rank, world)
-        elif args.scaling == "strong":           # ONE frame per step, its rows dealt to the ranks in contiguous blocks
+        if args.scaling == "strong":           # ONE frame per step, its rows dealt to the ranks in contiguous blocks
             o, d = pinhole_rays(H, W, orbit(k, N_VIEWS))
             if args.random_rays:
                 sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(1000 + k))[:args.rays]

@@ -302,6 +302,7 @@ static void launch_sdf(int variant, unsigned grid, cudaStream_t s, const PLMeta 
     if (variant == 1) k_fused_sdf_tc<MODE, true, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
     else if (variant == 2) k_fused_sdf_tc<MODE, false, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
     else if (variant == 3) k_fused_sdf_tc<MODE, true, 1><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
+    else if (variant == 5) k_fused_sdf_tc<MODE, true, 4><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);   // experiment: four levels (32 loads) per trip
     else if (variant == 4 && plmeta_pairable(m, g)) k_fused_sdf_tc<MODE, true, 2, true><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);   // experiment: paired corner loads
     else k_fused_sdf_tc<MODE, false, 2><<<grid, kTile, 0, s>>>(m, g, d, x, ro, rd, ridx, t, n, ml, sdf, pi, pr, np, oc, nd);
 }
