@@ -560,6 +560,9 @@ class StaticFrame:
             return self
         was = L.KERNEL_TIMER.enabled
         L.KERNEL_TIMER.enabled = False                      # events cannot be recorded into a capture
+        import gc
+        gc.collect()                                        # autograd graphs of earlier (default-stream) backward passes that only the cycle collector
+        #                                                     frees keep the parameters' AccumulateGrad nodes on the default stream -> capture error
         try:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
