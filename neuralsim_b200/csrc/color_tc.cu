@@ -366,6 +366,10 @@ k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev n
 //   dh  = dZ1 . R1[:, h columns]   (M128 N32 K64)    A = T block 1,                     B = R1h^T tile
 //   XA += [dZ2 | dZ1]^T . [Y1 | 1]           (M128 N72 K128, MN-major): rows 0..63  = [dR2 | drb2]
 //   XB += [dZ1 | y2 ]^T . [X | 1 gy3 0..]    (M128 N72 K128, MN-major): rows 0..63  = [dR1 | drb1], rows 64..127, cols 65..67 = dR3^T
+// TMA = true: the three saved activation tiles of a point tile (X, Y1, Y2: 3 x 16 KB, each contiguous in global memory and in shared
+// memory) are fetched by the bulk async copy engine (cp.async.bulk -> mbarrier), issued by one thread; the fetch of the NEXT tile starts as soon
+// as the last MMA that reads the current tiles has completed, so it overlaps the epilogue, the dh store and the next prologue.
+template <bool TMA>
 __global__ void __launch_bounds__(kTile)
 k_color_rad_bwd(const ColorNetDev net, const uint8_t *__restrict__ Xt, const uint8_t *__restrict__ Y1t, const uint8_t *__restrict__ Y2t,
                 const float *__restrict__ rgb, const float *__restrict__ g_rgb, int64_t n, float *__restrict__ dh_out,
@@ -383,6 +387,7 @@ k_color_rad_bwd(const ColorNetDev net, const uint8_t *__restrict__ Xt, const uin
     __shared__ float sR3[3][XW];
     __shared__ float sdb3[3];
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar_ld;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -406,6 +411,7 @@ k_color_rad_bwd(const ColorNetDev net, const uint8_t *__restrict__ Xt, const uin
     if (tid == 0) {
         sdb3[0] = sdb3[1] = sdb3[2] = 0.f;
         tc::mbar_init(&mbar, 1);
+        tc::mbar_init(&mbar_ld, 1);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
@@ -419,19 +425,31 @@ k_color_rad_bwd(const ColorNetDev net, const uint8_t *__restrict__ Xt, const uin
     const uint32_t r2t_addr = tc::smem_u32(sR2T), r1h_addr = tc::smem_u32(sR1h);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     constexpr uint32_t cDY1 = 0, cDH = 64, cXA = 96, cXB = 176;
-    uint32_t phase = 0;
+    uint32_t phase = 0, ld_phase = 0;
     bool first_tile = true;
 
     const int64_t n_tiles = (n + kTile - 1) / kTile;
+    auto fetch = [&](int64_t tile) {                          // one thread: 48 KB of saved activations -> the three shared-memory tiles
+        tc::mbar_arrive_expect_tx(&mbar_ld, 3 * kTileBytes);
+        tc::tma_load_bulk(sT + 2 * kTileBytes, Y2t + tile * kTileBytes, kTileBytes, &mbar_ld);
+        tc::tma_load_bulk(sY1, Y1t + tile * kTileBytes, kTileBytes, &mbar_ld);
+        tc::tma_load_bulk(sXe, Xt + tile * kTileBytes, kTileBytes, &mbar_ld);
+    };
+    if (TMA && tid == 0 && (int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * kTile + tid;
         const bool valid = i < n;
-        const uint8_t *xt = Xt + tile * kTileBytes, *y1t = Y1t + tile * kTileBytes, *y2t = Y2t + tile * kTileBytes;
+        if (TMA) {
+            tc::mbar_wait(&mbar_ld, ld_phase);                // the tiles of this iteration have landed
+            ld_phase ^= 1;
+        } else {
+            const uint8_t *xt = Xt + tile * kTileBytes, *y1t = Y1t + tile * kTileBytes, *y2t = Y2t + tile * kTileBytes;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-            *reinterpret_cast<uint4 *>(sT + 2 * kTileBytes + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(y2t + c * kChunk + tid * 16);
-            *reinterpret_cast<uint4 *>(sY1 + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(y1t + c * kChunk + tid * 16);
-            *reinterpret_cast<uint4 *>(sXe + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(xt + c * kChunk + tid * 16);
+            for (int c = 0; c < 8; ++c) {
+                *reinterpret_cast<uint4 *>(sT + 2 * kTileBytes + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(y2t + c * kChunk + tid * 16);
+                *reinterpret_cast<uint4 *>(sY1 + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(y1t + c * kChunk + tid * 16);
+                *reinterpret_cast<uint4 *>(sXe + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(xt + c * kChunk + tid * 16);
+            }
         }
         float gy[3] = {0.f, 0.f, 0.f};
         if (valid && g_rgb) {
@@ -506,6 +524,12 @@ k_color_rad_bwd(const ColorNetDev net, const uint8_t *__restrict__ Xt, const uin
         tc::mbar_wait(&mbar, phase);
         phase ^= 1;
         tc::fence_after_sync();
+        if (TMA && tid == 0 && tile + gridDim.x < n_tiles) {
+            // every reader of the three tiles is done: the threads' own reads precede the __syncthreads before the MMAs above, and those MMAs
+            // (the last readers) have completed -> the next tile's activations may overwrite them while this tile is finished
+            tc::fence_async_smem();
+            fetch(tile + gridDim.x);
+        }
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             float dh[8];
@@ -806,6 +830,8 @@ inline unsigned tiles_grid(int64_t n, int ctas_per_sm) {
 }
 }  // namespace
 
+namespace nsb { extern std::atomic<int> g_opt_color_tma; }
+
 extern "C" int64_t nsb_color_tile_bytes(int64_t n) { return ((n + kTile - 1) / kTile) * (int64_t)kTileBytes; }
 
 extern "C" int nsb_fused_color_fwd(const nsb_lotd_meta *meta, const void *params_half, const nsb_color_net *net, const float *x, const float *rays_o,
@@ -850,9 +876,14 @@ extern "C" int nsb_fused_color_bwd(const nsb_lotd_meta *meta, const void *params
     const float *dh = nullptr;
     if (g_rgb) {
         constexpr int kSmemR = 3 * kTileBytes + 2 * kTile * 80 * 2 + XW * XW * 2 + NF * XW * 2 + 1024;
-        opt_in_smem(k_color_rad_bwd, kSmemR);
-        k_color_rad_bwd<<<tiles_grid(n, 2), kTile, kSmemR, s>>>(d, (const uint8_t *)act_x, (const uint8_t *)act_y1, (const uint8_t *)act_y2, rgb, g_rgb, n,
-                                                                dh_scratch, d_R1, d_rb1, d_R2, d_rb2, d_R3, d_rb3, dn.a);
+        opt_in_smem(k_color_rad_bwd<true>, kSmemR);
+        opt_in_smem(k_color_rad_bwd<false>, kSmemR);
+        if (g_opt_color_tma.load())
+            k_color_rad_bwd<true><<<tiles_grid(n, 2), kTile, kSmemR, s>>>(d, (const uint8_t *)act_x, (const uint8_t *)act_y1, (const uint8_t *)act_y2, rgb, g_rgb, n,
+                                                                          dh_scratch, d_R1, d_rb1, d_R2, d_rb2, d_R3, d_rb3, dn.a);
+        else
+            k_color_rad_bwd<false><<<tiles_grid(n, 2), kTile, kSmemR, s>>>(d, (const uint8_t *)act_x, (const uint8_t *)act_y1, (const uint8_t *)act_y2, rgb, g_rgb, n,
+                                                                           dh_scratch, d_R1, d_rb1, d_R2, d_rb2, d_R3, d_rb3, dn.a);
         if (int rc = check_launch("nsb_fused_color_bwd(radiance)")) return rc;
         dh = dh_scratch;
     }
