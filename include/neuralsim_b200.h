@@ -368,12 +368,23 @@ int nsb_fused_color_bwd(const nsb_lotd_meta *meta_host, const void *params_half,
                         float *d_b1, float *d_W2, float *d_b2, float *d_R1, float *d_rb1, float *d_R2, float *d_rb2, float *d_R3,
                         float *d_rb3, void *stream);
 
-/* ---------------------------------------------------------------- EXPERIMENTAL (csrc/ray_upsample.cu; not on the default path)
- * The no-grad up-sampling stages of neus_ray_query_march_occ_multi_upsample_compressed (neus_ray_query.py:861-905) for every hit ray as ONE
+/* ---------------------------------------------------------------- the persistent per-ray kernel (csrc/ray_upsample.cu)
+ * The no-grad up-sampling half of neus_ray_query_march_occ_multi_upsample_compressed (neus_ray_query.py:861-905) for every hit ray as ONE
  * persistent kernel: sdf of the marched samples, then per stage cdf -> n_fine[i] inverse-cdf samples -> sdf -> merge, with the ray's samples in
- * shared memory.  fine_all[n_hit, sum(n_fine)] = cat of the stages' samples; overflow[n_hit] (caller zero-fills) is set for rays that do not fit
- * the per-ray capacity (their rows of fine_all are not written).  n_fine / inv_s_stage / u_stage are HOST arrays of n_stage entries; u_stage[i]
- * points to DEVICE memory with the n_fine[i] quantiles of stage i. */
+ * shared memory (replaces 11 launches of the stage kernels above; bit-identical results: same device functions).
+ * fine_all[n_hit, sum(n_fine)] = cat of the stages' samples.  n_fine / inv_s_stage / u_stage are HOST arrays of n_stage entries; u_stage[i]
+ * points to DEVICE memory with the n_fine[i] quantiles of stage i (linspace(0,1,n+2)[1:-1]: `perturb=False`).
+ * A ray with more marched samples than the shared-memory capacity works in its slice of `scratch` (nsb_upsample_rays_scratch_floats(n_hit
+ * capacity, long_cap) floats; long_cap >= max marched samples per ray + sum of the merged stages); overflow[n_hit] (caller zero-fills) is
+ * set only for a ray that exceeds long_cap (or the shared-memory capacity when scratch == NULL).  collect: in-kernel sample collection of the
+ * training-time SDF queries (may be NULL).  Count-aware (nsb_bind_device_counts: n_hit). */
+int nsb_upsample_rays(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host, const float *rays_o,
+                      const float *rays_d, const float *t_starts, const int64_t *pack_infos, const int64_t *ridx_hit, int64_t n_hit,
+                      int32_t max_level, int32_t n_stage, const int32_t *n_fine_host, const float *inv_s_stage_host,
+                      const float *const *u_stage_host, int32_t use_estimate_alpha, float early_stop_eps, float alpha_thre, float *fine_all,
+                      int32_t *overflow, float *scratch, int32_t long_cap, const nsb_occ_collect *collect, void *stream);
+int64_t nsb_upsample_rays_scratch_floats(int64_t n_hit_capacity, int32_t long_cap);
+/* the same without scratch / collection (rays beyond the shared-memory capacity are flagged in `overflow`) */
 int nsb_upsample_persistent(const nsb_lotd_meta *meta_host, const void *params_half, const nsb_sdf_decoder *dec_host, const float *rays_o,
                             const float *rays_d, const float *t_starts, const int64_t *pack_infos, const int64_t *ridx_hit, int64_t n_hit,
                             int32_t max_level, int32_t n_stage, const int32_t *n_fine, const float *inv_s_stage, const float *const *u_stage,

@@ -1,12 +1,14 @@
-// EXPERIMENT (not on the default path; round-2 groundwork, profiles/NEXT_persistent_ray_kernel.md): the no-grad up-sampling half of the
-// NeuS query as ONE persistent kernel.  For every ray that marched into occupied voxels it replaces, per up-sampling stage, the launches
+// The no-grad up-sampling half of the NeuS query as ONE persistent kernel (the default when the quantiles are not perturbed).
+// For every ray that marched into occupied voxels it replaces, per up-sampling stage, the launches
 //   k_fused_sdf_tc (sdf of the marched / new samples) -> k_upsample_cdf -> k_invert_cdf_shared_u -> k_merge_vals
 // (graphics/neus.py:_query_fused, reference neus_ray_query.py:861-905) and keeps the ray's samples in shared memory in between.
 // A CTA of 128 threads owns a group of 4 consecutive hit rays: warp w <-> ray w for the per-ray stages (the bodies are the stand-alone kernels'
 // own device functions, neus_device.cuh, so the results are bit-identical by construction); for the SDF evaluations the four rays' pending samples
 // are concatenated into 128-point tiles of the usual gather -> tcgen05 -> SFU pipeline (sdf_of_tile, fused_tc_common.cuh).
-// Output: fine[n_hit, sum(n_fine)] -- what `torch.cat(fine_stages, -1)` is on the multi-kernel path.  Rays whose samples do not fit the
-// per-ray shared-memory capacity are flagged in `overflow` and left to the multi-kernel path.
+// Output: fine[n_hit, sum(n_fine)] -- what `torch.cat(fine_stages, -1)` is on the multi-kernel path.  A ray whose samples do not fit the
+// per-ray shared-memory capacity (kCap) works on a slice of a global scratch buffer instead (same code: the stage bodies take plain
+// pointers); `overflow` is only raised for a ray longer than that slice (`long_cap`, sized from max_steps by the caller: cannot happen then).
+// Training-time sample collection (accel.collect_samples on every SDF query, renderer_mixin.py:154-164) is done in-kernel as in k_fused_sdf_tc.
 #include "fused_tc_common.cuh"
 #include "neus_device.cuh"
 
@@ -92,7 +94,9 @@ __global__ void __launch_bounds__(kTile)
 k_upsample_persistent(const PLMeta m, const __half *__restrict__ grid, const DecoderDevTC dec, const float *__restrict__ rays_o,
                       const float *__restrict__ rays_d, const float *__restrict__ t_starts, const int64_t *__restrict__ pack_infos,
                       const int64_t *__restrict__ ridx_hit, int64_t n_hit, int max_level, const UpsampleArgs ua, float *__restrict__ fine_all,
-                      int nf_total, int32_t *__restrict__ overflow) {
+                      int nf_total, int32_t *__restrict__ overflow, float *__restrict__ scratch, int long_cap, const OccCollect oc,
+                      const int64_t *__restrict__ n_dev) {
+    n_hit = eff_n(n_hit, n_dev);
     __shared__ __align__(1024) uint8_t sA[kTile * NF * 2];
     __shared__ __align__(1024) uint8_t sB[HW * NF * 2];
     __shared__ float sb1[HW], sW2[HW];
@@ -103,6 +107,7 @@ k_upsample_persistent(const PLMeta m, const __half *__restrict__ grid, const Dec
     __shared__ float s_fine[kG][kMaxFine], s_fsdf[kG][kMaxFine];
     __shared__ float s_o[kG][3], s_d[kG][3];
     __shared__ int s_n[kG];
+    __shared__ float *p_t[2][kG], *p_sdf[2][kG], *p_cdf[kG];          // where ray q's samples live: shared memory, or its slice of `scratch`
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     stage_W1(dec, sB, tid);
@@ -135,17 +140,28 @@ k_upsample_persistent(const PLMeta m, const __half *__restrict__ grid, const Dec
         if (j < n_hit) {
             first = pack_infos[2 * j];
             n = (int)pack_infos[2 * j + 1];
-            if (n > room) {                              // does not fit: the multi-kernel path handles this ray
-                if (lane == 0) overflow[j] = 1;
-                n = 0;
-            }
         }
+        bool in_smem = n <= room;
+        if (!in_smem && (scratch == nullptr || n > long_cap - (kCap - room))) {      // longer than the scratch slice: flagged, row left undefined
+            if (lane == 0) overflow[j] = 1;
+            n = 0;
+            in_smem = true;
+        }
+        if (lane == 0) {
+            float *g = scratch ? scratch + ((size_t)blockIdx.x * kG + warp) * 5 * (size_t)long_cap : nullptr;
+            p_t[0][warp] = in_smem ? s_t[0][warp] : g;
+            p_t[1][warp] = in_smem ? s_t[1][warp] : g + long_cap;
+            p_sdf[0][warp] = in_smem ? s_sdf[0][warp] : g + 2 * (size_t)long_cap;
+            p_sdf[1][warp] = in_smem ? s_sdf[1][warp] : g + 3 * (size_t)long_cap;
+            p_cdf[warp] = in_smem ? s_cdf[warp] : g + 4 * (size_t)long_cap;
+        }
+        __syncwarp();
         if (n > 0 && lane < 3) {
             const int64_t ray = ridx_hit[j];
             s_o[warp][lane] = rays_o[ray * 3 + lane];
             s_d[warp][lane] = rays_d[ray * 3 + lane];
         }
-        for (int k = lane; k < n; k += 32) s_t[0][warp][k] = t_starts[first + k];
+        for (int k = lane; k < n; k += 32) p_t[0][warp][k] = t_starts[first + k];
         if (lane == 0) s_n[warp] = n;
         __syncthreads();
         int cur = 0;
@@ -158,14 +174,17 @@ k_upsample_persistent(const PLMeta m, const __half *__restrict__ grid, const Dec
                 if (valid) { while (r >= s_n[q]) { r -= s_n[q]; ++q; } }
                 float xs[3] = {0.f, 0.f, 0.f};
                 if (valid) {
-                    const float tt = s_t[0][q][r];
+                    const float tt = p_t[0][q][r];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) xs[c] = __fmaf_rn(s_d[q][c], tt, s_o[q][c]);
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) xs[c] = fminf(fmaxf(__fmaf_rn(xs[c], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
                 const float v = sdf_of_tile<true, 2, false>(ctx, xs, tid, phase);
-                if (valid) s_sdf[0][q][r] = v;
+                if (valid) {
+                    p_sdf[0][q][r] = v;
+                    if (oc.pcl) occ_collect_point(oc, xs, v);
+                }
             }
             __syncthreads();
         }
@@ -174,9 +193,9 @@ k_upsample_persistent(const PLMeta m, const __half *__restrict__ grid, const Dec
             const int nf = ua.n_fine[i];
             // ---- per ray: cdf of the up-sampling weights, then the nf inverse-cdf samples
             if (n > 0) {
-                warp_upsample_cdf(s_sdf[cur][warp], s_t[cur][warp], n, ua.inv_s[i], ua.use_estimate, ua.eps, ua.thre, s_cdf[warp], lane);
+                warp_upsample_cdf(p_sdf[cur][warp], p_t[cur][warp], n, ua.inv_s[i], ua.use_estimate, ua.eps, ua.thre, p_cdf[warp], lane);
                 for (int q = lane; q < nf; q += 32) {
-                    const float f = invert_cdf_one(s_t[cur][warp], s_cdf[warp], (uint32_t)n, ua.u[i][q]);
+                    const float f = invert_cdf_one(p_t[cur][warp], p_cdf[warp], (uint32_t)n, ua.u[i][q]);
                     s_fine[warp][q] = f;
                     fine_all[j * nf_total + off + q] = f;
                 }
@@ -197,12 +216,15 @@ k_upsample_persistent(const PLMeta m, const __half *__restrict__ grid, const Dec
 #pragma unroll
                 for (int c = 0; c < 3; ++c) xs[c] = fminf(fmaxf(__fmaf_rn(xs[c], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
                 const float v = sdf_of_tile<true, 2, false>(ctx, xs, tid, phase);
-                if (valid) s_fsdf[q][k] = v;
+                if (valid) {
+                    s_fsdf[q][k] = v;
+                    if (oc.pcl) occ_collect_point(oc, xs, v);
+                }
             }
             __syncthreads();
             // ---- per ray: merge the new samples (and their sdf) into the ray
             if (n > 0) {
-                warp_merge(s_t[cur][warp], s_sdf[cur][warp], n, s_fine[warp], s_fsdf[warp], nf, s_t[cur ^ 1][warp], s_sdf[cur ^ 1][warp], lane);
+                warp_merge(p_t[cur][warp], p_sdf[cur][warp], n, s_fine[warp], s_fsdf[warp], nf, p_t[cur ^ 1][warp], p_sdf[cur ^ 1][warp], lane);
                 n += nf;
             }
             cur ^= 1;
@@ -222,6 +244,21 @@ extern "C" int nsb_upsample_persistent(const nsb_lotd_meta *meta, const void *pa
                                        int32_t max_level, int32_t n_stage, const int32_t *n_fine, const float *inv_s_stage, const float *const *u_stage,
                                        int32_t use_estimate_alpha, float early_stop_eps, float alpha_thre, float *fine_all, int32_t *overflow,
                                        void *stream) {
+    return nsb_upsample_rays(meta, params_half, dec, rays_o, rays_d, t_starts, pack_infos, ridx_hit, n_hit, max_level, n_stage, n_fine, inv_s_stage, u_stage,
+                             use_estimate_alpha, early_stop_eps, alpha_thre, fine_all, overflow, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int64_t nsb_upsample_rays_scratch_floats(int64_t n_hit_cap, int32_t long_cap) {
+    const int64_t groups = (n_hit_cap + kG - 1) / kG, wave = (int64_t)sm_count() * 5;
+    return (groups < wave ? groups : wave) * kG * 5 * (int64_t)long_cap;
+}
+
+extern "C" int nsb_upsample_rays(const nsb_lotd_meta *meta, const void *params_half, const nsb_sdf_decoder *dec, const float *rays_o,
+                                 const float *rays_d, const float *t_starts, const int64_t *pack_infos, const int64_t *ridx_hit, int64_t n_hit,
+                                 int32_t max_level, int32_t n_stage, const int32_t *n_fine, const float *inv_s_stage, const float *const *u_stage,
+                                 int32_t use_estimate_alpha, float early_stop_eps, float alpha_thre, float *fine_all, int32_t *overflow,
+                                 float *scratch, int32_t long_cap, const nsb_occ_collect *collect, void *stream) {
+    const DevCounts dn = take_counts();
     if (n_hit == 0) return 0;
     NSB_REQUIRE(meta && params_half && dec && rays_o && rays_d && t_starts && pack_infos && ridx_hit && n_fine && inv_s_stage && u_stage && fine_all && overflow,
                 "nsb_upsample_persistent: NULL argument");
@@ -247,8 +284,11 @@ extern "C" int nsb_upsample_persistent(const nsb_lotd_meta *meta, const void *pa
     NSB_REQUIRE(merged < kCap, "nsb_upsample_persistent: the merged stages alone exceed the per-ray capacity");
     DecoderDevTC d{(const __half *)dec->W1, (const __half *)dec->b1, (const __half *)dec->W2, (const __half *)dec->b2, dec->width, dec->beta};
     const int64_t groups = (n_hit + kG - 1) / kG, wave = (int64_t)sm_count() * 5;
+    NSB_REQUIRE(scratch == nullptr || long_cap > kCap, "nsb_upsample_rays: long_cap must exceed the shared-memory capacity (%d)", kCap);
+    OccCollect oc{nullptr, 1, 1, 1, 0.f};
+    if (collect && collect->grid_pcl) oc = OccCollect{collect->grid_pcl, collect->res[0], collect->res[1], collect->res[2], collect->inv_s};
     k_upsample_persistent<<<(unsigned)(groups < wave ? groups : wave), kTile, 0, (cudaStream_t)stream>>>(
         m, (const __half *)params_half, d, rays_o, rays_d, t_starts, pack_infos, ridx_hit, n_hit, max_level < 0 ? -1 : max_level, ua, fine_all, nf_total,
-        overflow);
-    return check_launch("nsb_upsample_persistent");
+        overflow, scratch, long_cap, oc, dn.a);
+    return check_launch("nsb_upsample_rays");
 }

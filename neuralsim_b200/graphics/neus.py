@@ -28,6 +28,9 @@ from . import neus_fused
 # pack_ops / elementwise calls (same maths; kept for the parity tests and as documentation of what is fused).
 FUSED_STAGES = True
 import os as _os
+# True: the no-grad half of the fused query (sdf of the marched samples + the up-sampling stages) is ONE persistent per-ray kernel
+# (csrc/ray_upsample.cu); False / perturb=True: one launch per stage (same values: tests/test_neus_fused_gpu.py)
+PERSISTENT_UPSAMPLE = _os.environ.get("NSB_PERSISTENT_UPSAMPLE", "1") != "0"
 MARCHED_TILED = _os.environ.get("NSB_MARCHED_TILED", "0") != "0"     # measured: 0.71 ms ray-major vs 0.99 ms ray-tiled per frame (profiles/README.md)
 
 __all__ = ["neus_cdf", "neus_ray_cdf_to_alpha", "neus_ray_sdf_to_alpha", "neus_ray_sdf_to_vw", "neus_packed_cdf_to_alpha",
@@ -123,6 +126,19 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, perturb=False, 
         torch.rand(depth_samples.shape, dtype=depth_samples.dtype, device=depth_samples.device)
     pack_infos = pinfo_march
     coherent = bool(ray_tested.get("rays_coherent", False))      # image-ordered rays: ray-tiled traversal inside the SDF kernel
+    surf = getattr(model, "implicit_surface", None)
+    if PERSISTENT_UPSAMPLE and not perturb and surf is not None and getattr(surf, "_fusable", lambda: False)():
+        # the whole no-grad half in ONE persistent per-ray kernel (csrc/ray_upsample.cu); same values as the stage kernels below
+        grid16, dec = surf._fused_state()
+        accel = getattr(model, "accel", None)
+        collect = accel.occ.collect_struct() if (model.training and accel is not None) else None
+        fine_all, _overflow = neus_fused.upsample_rays(surf.encoding.meta, grid16, dec, ridx_hit, pack_infos, depth_samples, rays_o, rays_d,
+                                                       [upsample_inv_s * f for f in factors], num_fine, max_level=surf._ml(getattr(model, "max_level", None)),
+                                                       max_steps=mc["max_steps"], use_estimate_alpha=use_estimate_alpha, collect=collect)
+        with torch.no_grad():
+            d1, mid, ridx_all, pinfo = neus_fused.assemble_boundary(depths_coarse_1.contiguous(), ridx_hit, fine_all, run_len=list(num_fine))
+        return _query_fused_tail(model, ray_tested, view_dirs, rays_h_appear, rays_o, rays_d, rays_inds, d1, mid, ridx_all, pinfo, pinfo_march, coherent, dtype,
+                                 with_rgb=with_rgb, with_normal=with_normal, nablas_has_grad=nablas_has_grad, forward_inv_s=forward_inv_s)
     with torch.no_grad():
         # marched packs are ragged (20-100 samples per ray): tiles of 32 rays are padded to the longest and the samples of one ray are
         # already close together, so the ray-major order wins here (A/B switch MARCHED_TILED); the boundary and fine queries have
@@ -143,6 +159,13 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, perturb=False, 
                 depth_samples, sdf, pack_infos = neus_fused.merge_sorted_vals(depth_samples, sdf, pack_infos, fine, sdf_fine)
         fine_all = torch.cat(fine_stages, dim=-1) if n_stage > 1 else fine_stages[0]
         d1, mid, ridx_all, pinfo = neus_fused.assemble_boundary(depths_coarse_1.contiguous(), ridx_hit, fine_all.contiguous(), run_len=[f.shape[1] for f in fine_stages])
+    return _query_fused_tail(model, ray_tested, view_dirs, rays_h_appear, rays_o, rays_d, rays_inds, d1, mid, ridx_all, pinfo, pinfo_march, coherent, dtype,
+                             with_rgb=with_rgb, with_normal=with_normal, nablas_has_grad=nablas_has_grad, forward_inv_s=forward_inv_s)
+
+
+def _query_fused_tail(model, ray_tested, view_dirs, rays_h_appear, rays_o, rays_d, rays_inds, d1, mid, ridx_all, pinfo, pinfo_march, coherent, dtype, *,
+                      with_rgb, with_normal, nablas_has_grad, forward_inv_s):
+    """boundary SDF (grad) -> alpha -> compression -> colour / normal query: the second half of `_query_fused`"""
     sdf_b = model.forward_sdf_on_rays(ridx_all, d1, rays_o, rays_d, packs=(pinfo, None) if coherent else None)["sdf"].to(dtype)
     comp = neus_fused.neus_alpha_compact(sdf_b, forward_inv_s, pinfo, ridx_all, mid, rays_inds)
     if comp is None:

@@ -17,7 +17,7 @@ import torch
 from .. import _lib as L
 
 __all__ = ["upsample_cdf", "sample_cdf_uniform", "neus_alpha_compress", "neus_alpha_compact", "composite", "scan_counts", "merge_sorted_vals",
-           "assemble_boundary", "march_lean"]
+           "assemble_boundary", "march_lean", "upsample_rays"]
 
 _U_CACHE = {}
 
@@ -323,10 +323,54 @@ def composite(alpha, t, pack_infos, rgb=None, nablas=None, normalize_depth=True,
     return vw, mask, depth, (rgb_o if rgb is not None else None), (nab_o if nablas is not None else None)
 
 
+def _quantiles(n, dev):
+    key = (n, dev)
+    u = _U_CACHE.get(key)
+    if u is None:
+        u = _U_CACHE[key] = torch.linspace(0., 1., n + 2, device=dev, dtype=torch.float32)[1:-1].contiguous()
+    return u
+
+
+@torch.no_grad()
+def upsample_rays(meta, grid16, dec, ridx_hit, pack_infos, t_starts, rays_o, rays_d, inv_s_stages, num_fine, *, max_level, max_steps, use_estimate_alpha=False,
+                  early_stop_eps=1e-4, alpha_thre=0.0, collect=None, count=None):
+    """All up-sampling stages of the hit rays in ONE persistent kernel (csrc/ray_upsample.cu): sdf of the marched samples, then per stage
+    cdf -> inverse-cdf samples -> sdf -> merge, the ray's samples in shared memory (long rays: a slice of a global scratch buffer).
+    Replaces, with bit-identical results, the 11 launches `upsample_cdf / sample_cdf_uniform / fused_sdf_rays / merge_sorted_vals` make for
+    three stages.  inv_s_stages[i] = upsample_inv_s * factor_i; num_fine: odd-ised counts.  `count` = (cnt tensor, slot): n_hit lives on the
+    device and `ridx_hit.shape[0]` is the capacity.  -> (fine_all [n_hit, sum(num_fine)], overflow int32 [n_hit] (all zero unless a ray
+    marched more than max_steps samples))."""
+    n_hit, dev = ridx_hit.shape[0], t_starts.device
+    n_stage = len(num_fine)
+    us = [_quantiles(int(n), dev) for n in num_fine]
+    fine_all = torch.empty(n_hit, int(sum(num_fine)), dtype=torch.float32, device=dev)
+    overflow = torch.zeros(n_hit, dtype=torch.int32, device=dev)
+    long_cap = int(max_steps) + int(sum(num_fine[:-1])) + 64
+    lib = L.lib()
+    lib.nsb_upsample_rays_scratch_floats.restype = ctypes.c_int64
+    scratch = torch.empty(int(lib.nsb_upsample_rays_scratch_floats(L.c_i64(n_hit), L.c_i32(long_cap))), dtype=torch.float32, device=dev)
+    nf = (ctypes.c_int32 * n_stage)(*[int(n) for n in num_fine])
+    invs = (ctypes.c_float * n_stage)(*[float(v) for v in inv_s_stages])
+    up = (ctypes.c_void_p * n_stage)(*[u.data_ptr() for u in us])
+    if count is not None:
+        lib.nsb_bind_device_counts(ctypes.c_void_p(count[0].data_ptr() + 8 * count[1]), ctypes.c_void_p(0))
+    try:
+        with L.KERNEL_TIMER.time("ray_upsample", n_hit):
+            rc = lib.nsb_upsample_rays(meta.c_ref, L.ptr(grid16, "f16"), ctypes.byref(dec), L.ptr(rays_o, "f32"), L.ptr(rays_d, "f32"), L.ptr(t_starts, "f32"),
+                                       L.ptr(pack_infos, "i64"), L.ptr(ridx_hit, "i64"), L.c_i64(n_hit), L.c_i32(max_level), L.c_i32(n_stage), nf, invs, up,
+                                       L.c_i32(1 if use_estimate_alpha else 0), L.c_f32(early_stop_eps), L.c_f32(alpha_thre), L.ptr(fine_all), L.ptr(overflow),
+                                       L.ptr(scratch), L.c_i32(long_cap), ctypes.byref(collect) if collect is not None else None, L.stream_ptr())
+    finally:
+        if count is not None:
+            lib.nsb_bind_device_counts(ctypes.c_void_p(0), ctypes.c_void_p(0))
+    L.check(rc, "upsample_rays")
+    return fine_all, overflow
+
+
 @torch.no_grad()
 def upsample_persistent(surface, ridx_hit, pack_infos, t_starts, rays_o, rays_d, inv_s_stages, num_fine, use_estimate_alpha=False,
                         early_stop_eps=1e-4, alpha_thre=0.0, max_level=None):
-    """EXPERIMENT (csrc/ray_upsample.cu, not on the default path): all up-sampling stages of the hit rays in one persistent kernel.
+    """`upsample_rays` without the scratch for long rays (they are flagged in `overflow` instead): the round-1 entry point, kept for its test.
     surface: LoTDSDF (fused query state); inv_s_stages[i] = upsample_inv_s * factor_i; num_fine: odd-ised sample counts per stage.
     -> (fine_all [n_hit, sum(num_fine)], overflow int32 [n_hit]: 1 = this ray did not fit, its row is undefined)."""
     grid16, dec = surface._fused_state()

@@ -383,10 +383,19 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
                   P(ridx_hit, "i64"), L.c_i64(R), P(bits), L.stream_ptr())
         ridx = ridx32.long()
         # ---------------- up-sampling (no grad)
-        sdf = torch.empty(march_cap, dtype=torch.float32, device=dev)
-        _sdf_launch(st.meta, st.grid16, st.dec, o_c, d_c, depth, sdf, ridx=ridx, ml=st.ml, collect=st.collect, cnt=cnt, slot=CNT_SLOTS["marched"])
-        fine_stages = []
-        for i, factor in enumerate(factors):
+        from . import neus as GN
+        fine_stages = None
+        if GN.PERSISTENT_UPSAMPLE:                           # ONE persistent per-ray kernel (csrc/ray_upsample.cu)
+            fine_all, _ovf = NF.upsample_rays(st.meta, st.grid16, st.dec, ridx_hit, pack_infos, depth, o_c, d_c, [upsample_inv_s * f for f in factors], num_fine,
+                                              max_level=st.ml, max_steps=max_steps, use_estimate_alpha=use_est, collect=st.collect, count=(cnt, CNT_SLOTS["hit"]))
+            factors_loop = []
+        else:
+            factors_loop = factors
+        sdf = torch.empty(march_cap if factors_loop else 1, dtype=torch.float32, device=dev)
+        if factors_loop:
+            fine_stages = []
+            _sdf_launch(st.meta, st.grid16, st.dec, o_c, d_c, depth, sdf, ridx=ridx, ml=st.ml, collect=st.collect, cnt=cnt, slot=CNT_SLOTS["marched"])
+        for i, factor in enumerate(factors_loop):
             cdf = torch.empty(march_cap, dtype=torch.float32, device=dev)
             _call(lib.nsb_neus_upsample_cdf, "neus_upsample_cdf", cnt, CNT_SLOTS["hit"], None, P(sdf, "f32"), P(depth, "f32"), P(pack_infos, "i64"), L.c_i64(R),
                   L.c_f32(upsample_inv_s * factor), ctypes.c_int(1 if use_est else 0), L.c_f32(1e-4), L.c_f32(0.0), P(cdf), L.stream_ptr())
@@ -412,7 +421,8 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
                 _call(lib.nsb_merge_sorted_vals, "merge_sorted_vals", cnt, CNT_SLOTS["hit"], None, P(depth, "f32"), P(sdf, "f32"), P(pack_infos, "i64"),
                       P(fine, "f32"), P(sdf_fine, "f32"), L.c_i64(R), L.c_i32(nf), P(dep_m), P(sdf_m), P(pim), L.stream_ptr())
                 depth, sdf, pack_infos = dep_m, sdf_m, pim
-        fine_all = (torch.cat(fine_stages, dim=-1) if n_stage > 1 else fine_stages[0]).contiguous()
+        if fine_stages is not None:
+            fine_all = (torch.cat(fine_stages, dim=-1) if n_stage > 1 else fine_stages[0]).contiguous()
         d1 = torch.empty(S_cap, dtype=torch.float32, device=dev)
         mid = torch.empty(S_cap, dtype=torch.float32, device=dev)
         ridx_all = torch.empty(S_cap, dtype=torch.int64, device=dev)
