@@ -498,7 +498,8 @@ class StaticFrame:
         frame.check()                                           # optional: one D2H of the counts; re-captures with larger arenas on overflow
 
     The first call probes the sizes with the host-sized path (SingleVolumeRenderer.ray_query, no grad), sizes the arenas with `slack`,
-    warms up and captures.  Gradients are accumulated into `p.grad` (kept in place; `zero_grads=True` zeroes them inside the graph)."""
+    warms up and captures.  Gradients are ACCUMULATED into an existing `p.grad` (in place; `zero_grads=True` or a `pre_hook` zeroes them inside
+    the graph); a parameter without `.grad` gets the step's own gradient buffer (= the gradient of the latest step)."""
 
     def __init__(self, model, n_rays, loss_fn=None, *, near=None, far=None, with_rgb=True, with_normal=True, slack=1.5, march_cap=None, kept_cap=None,
                  coherent=None, use_graph=True, zero_grads=False, h_appear_dim=None, pre_hook=None):
@@ -558,7 +559,16 @@ class StaticFrame:
         if self.loss_fn is not None:
             loss = self.loss_fn(rendered)
             if loss.requires_grad:
-                loss.backward()
+                # gradients through autograd.grad + an explicit accumulation instead of loss.backward(): the parameters' AccumulateGrad nodes are
+                # bound to the stream they were first used on (usually the default stream, which cannot take part in a capture)
+                params = [p for p in self.model.parameters() if p.requires_grad]
+                for p, g in zip(params, torch.autograd.grad(loss, params, allow_unused=True)):
+                    if g is None:
+                        continue
+                    if p.grad is None:
+                        p.grad = g              # aliases the step's own buffer: holds the gradient of the latest step
+                    else:
+                        p.grad.add_(g)
             loss = loss.detach()
         return rendered, buffers, loss
 

@@ -61,8 +61,10 @@ class SingleVolumeRenderer:
                                   depth_use_normalized_vw=self.config["depth_use_normalized_vw"], nablas_key="nablas_in_world", fresh=fresh)
 
     def ray_query(self, model: LoTDNeuSModel, rays_o, rays_d, rays_h_appear=None, near=None, far=None, return_buffer=True,
-                  return_details=False) -> Dict:
-        """One chunk of rays: -> dict(rendered={rgb_volume, depth_volume, mask_volume, normals_volume}, volume_buffer, details)."""
+                  return_details=False, distant_model=None) -> Dict:
+        """One chunk of rays: -> dict(rendered={rgb_volume, depth_volume, mask_volume, normals_volume}, volume_buffer, details).
+        distant_model (fields/distant.py:LoTDNeRFDistant): the NeRF++ background of every shipped config -- queried from the close-range far
+        bound on, its buffer merged per ray with the close-range one before the integration (single_volume_renderer.py:273-375)."""
         cfg = self.config
         near = cfg["near"] if near is None else near
         far = cfg["far"] if far is None else far
@@ -75,10 +77,27 @@ class SingleVolumeRenderer:
         qcfg.update(with_rgb=cfg["with_rgb"], with_normal=cfg["with_normal"], perturb=cfg["perturb"])
         raw = model.ray_query(ray_tested=ray_tested, config=qcfg, return_buffer=True, return_details=return_details)
         vb = raw["volume_buffer"]
+        if vb["type"] != "empty" and "nablas" in vb:
+            # obj -> world rotation is the identity for a single static object (single_volume_renderer.py:262-276)
+            vb["nablas_in_world"] = vb["nablas"]
+        if distant_model is not None:
+            from .compose import compose_render
+            near_dv = rays_o.new_full([n], 0. if near is None else float(near))
+            if ray_tested["num_rays"] > 0:
+                near_dv[ray_tested["rays_inds"]] = ray_tested["far"]          # behind the close-range box (single_volume_renderer.py:286-290)
+            dv_rt = dict(rays_o=rays_o.detach(), rays_d=rays_d.detach(), near=near_dv, far=None, num_rays=n, rays_inds=torch.arange(n, device=device),
+                         rays_h_appear=rays_h_appear)
+            dv = distant_model.ray_query(ray_tested=dv_rt, config=dict(with_rgb=cfg["with_rgb"], perturb=cfg["perturb"]), return_buffer=True)["volume_buffer"]
+            # both buffers are depth-sorted per ray: their merge (merge_two_packs_sorted) == the per-ray sort of their union
+            merged, total = compose_render([vb, dv], n, with_rgb=cfg["with_rgb"], with_normal=cfg["with_normal"], training=self.training,
+                                           depth_use_normalized_vw=cfg["depth_use_normalized_vw"])
+            ret["rendered"] = merged
+            if return_buffer:
+                ret["volume_buffer"], ret["cr_volume_buffer"], ret["dv_volume_buffer"] = (total if total is not None else vb), vb, dv
+            if return_details:
+                ret["details"] = raw.get("details", {})
+            return ret
         if vb["type"] != "empty":
-            if "nablas" in vb:
-                # obj -> world rotation is the identity for a single static object (single_volume_renderer.py:262-276)
-                vb["nablas_in_world"] = vb["nablas"]
             self._volume_integration(vb, rendered, fresh=True)
         ret["rendered"] = rendered.materialise()
         if return_buffer:
@@ -88,15 +107,15 @@ class SingleVolumeRenderer:
         return ret
 
     def render(self, model: LoTDNeuSModel, rays_o, rays_d, rays_h_appear=None, near=None, far=None, rayschunk=None,
-               return_buffer=False, return_details=False) -> Dict:
+               return_buffer=False, return_details=False, distant_model=None) -> Dict:
         """Whole batch / image; with `rayschunk` > 0 the rays are processed in chunks (batchify_query, models/utils.py:441)."""
         chunk = self.config["rayschunk"] if rayschunk is None else rayschunk
         n = rays_o.shape[0]
         if not chunk or chunk >= n:
-            return self.ray_query(model, rays_o, rays_d, rays_h_appear, near, far, return_buffer, return_details)
+            return self.ray_query(model, rays_o, rays_d, rays_h_appear, near, far, return_buffer, return_details, distant_model)
         outs = []
         for s in range(0, n, chunk):
             e = min(s + chunk, n)
             ha = None if rays_h_appear is None else rays_h_appear[s:e]
-            outs.append(self.ray_query(model, rays_o[s:e], rays_d[s:e], ha, near, far, False, False)["rendered"])
+            outs.append(self.ray_query(model, rays_o[s:e], rays_d[s:e], ha, near, far, False, False, distant_model)["rendered"])
         return dict(rendered={k: torch.cat([o[k] for o in outs], 0) for k in outs[0]})
