@@ -28,9 +28,18 @@ from . import neus_fused
 # pack_ops / elementwise calls (same maths; kept for the parity tests and as documentation of what is fused).
 FUSED_STAGES = True
 import os as _os
-# True: the no-grad half of the fused query (sdf of the marched samples + the up-sampling stages) is ONE persistent per-ray kernel
-# (csrc/ray_upsample.cu); False / perturb=True: one launch per stage (same values: tests/test_neus_fused_gpu.py)
-PERSISTENT_UPSAMPLE = _os.environ.get("NSB_PERSISTENT_UPSAMPLE", "1") != "0"
+# The no-grad half of the fused query (sdf of the marched samples + the up-sampling stages) as ONE persistent per-ray kernel
+# (csrc/ray_upsample.cu) or as one launch per stage -- same values either way (tests/test_ray_upsample_gpu.py).  Measured on the B200
+# (profiles/r02d_*): the persistent kernel wins on small batches (4096 random rays: 0.819 vs 0.840 ms / step, 25 instead of 35 launches) and loses
+# on large ones (800x600 frame: 14.06 vs 13.30 ms; its 128-point tiles are filled by 4 rays' 9-sample stages to 28 %), so: True / False force it,
+# "auto" (default) takes it below PERSISTENT_MAX_RAYS tested rays.  perturb=True always runs the stage kernels.
+_pu = _os.environ.get("NSB_PERSISTENT_UPSAMPLE", "auto")
+PERSISTENT_UPSAMPLE = "auto" if _pu == "auto" else (_pu != "0")
+PERSISTENT_MAX_RAYS = 8192
+
+
+def use_persistent_upsample(n_rays: int) -> bool:
+    return (n_rays < PERSISTENT_MAX_RAYS) if PERSISTENT_UPSAMPLE == "auto" else bool(PERSISTENT_UPSAMPLE)
 MARCHED_TILED = _os.environ.get("NSB_MARCHED_TILED", "0") != "0"     # measured: 0.71 ms ray-major vs 0.99 ms ray-tiled per frame (profiles/README.md)
 
 __all__ = ["neus_cdf", "neus_ray_cdf_to_alpha", "neus_ray_sdf_to_alpha", "neus_ray_sdf_to_vw", "neus_packed_cdf_to_alpha",
@@ -127,7 +136,7 @@ def _query_fused(model, ray_tested, view_dirs, rays_h_appear, *, perturb=False, 
     pack_infos = pinfo_march
     coherent = bool(ray_tested.get("rays_coherent", False))      # image-ordered rays: ray-tiled traversal inside the SDF kernel
     surf = getattr(model, "implicit_surface", None)
-    if PERSISTENT_UPSAMPLE and not perturb and surf is not None and getattr(surf, "_fusable", lambda: False)():
+    if use_persistent_upsample(rays_o.shape[0]) and not perturb and surf is not None and getattr(surf, "_fusable", lambda: False)():
         # the whole no-grad half in ONE persistent per-ray kernel (csrc/ray_upsample.cu); same values as the stage kernels below
         grid16, dec = surf._fused_state()
         accel = getattr(model, "accel", None)

@@ -385,7 +385,7 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
         # ---------------- up-sampling (no grad)
         from . import neus as GN
         fine_stages = None
-        if GN.PERSISTENT_UPSAMPLE:                           # ONE persistent per-ray kernel (csrc/ray_upsample.cu)
+        if GN.use_persistent_upsample(R):                    # ONE persistent per-ray kernel (csrc/ray_upsample.cu): small batches (graphics/neus.py)
             fine_all, _ovf = NF.upsample_rays(st.meta, st.grid16, st.dec, ridx_hit, pack_infos, depth, o_c, d_c, [upsample_inv_s * f for f in factors], num_fine,
                                               max_level=st.ml, max_steps=max_steps, use_estimate_alpha=use_est, collect=st.collect, count=(cnt, CNT_SLOTS["hit"]))
             factors_loop = []
@@ -498,8 +498,9 @@ class StaticFrame:
         frame.check()                                           # optional: one D2H of the counts; re-captures with larger arenas on overflow
 
     The first call probes the sizes with the host-sized path (SingleVolumeRenderer.ray_query, no grad), sizes the arenas with `slack`,
-    warms up and captures.  Gradients are ACCUMULATED into an existing `p.grad` (in place; `zero_grads=True` or a `pre_hook` zeroes them inside
-    the graph); a parameter without `.grad` gets the step's own gradient buffer (= the gradient of the latest step)."""
+    warms up and captures.  Gradients are accumulated into `p.grad` (kept in place; `zero_grads=True` or a `pre_hook` zeroes them inside the graph).
+    Capture precondition (PyTorch): no autograd graph of an EARLIER backward on the default stream may still be referenced (a kept loss / rendered
+    tensor): it pins the parameters' AccumulateGrad nodes to the default stream, which cannot take part in a capture."""
 
     def __init__(self, model, n_rays, loss_fn=None, *, near=None, far=None, with_rgb=True, with_normal=True, slack=1.5, march_cap=None, kept_cap=None,
                  coherent=None, use_graph=True, zero_grads=False, h_appear_dim=None, pre_hook=None):
@@ -559,16 +560,7 @@ class StaticFrame:
         if self.loss_fn is not None:
             loss = self.loss_fn(rendered)
             if loss.requires_grad:
-                # gradients through autograd.grad + an explicit accumulation instead of loss.backward(): the parameters' AccumulateGrad nodes are
-                # bound to the stream they were first used on (usually the default stream, which cannot take part in a capture)
-                params = [p for p in self.model.parameters() if p.requires_grad]
-                for p, g in zip(params, torch.autograd.grad(loss, params, allow_unused=True)):
-                    if g is None:
-                        continue
-                    if p.grad is None:
-                        p.grad = g              # aliases the step's own buffer: holds the gradient of the latest step
-                    else:
-                        p.grad.add_(g)
+                loss.backward()
             loss = loss.detach()
         return rendered, buffers, loss
 

@@ -69,7 +69,7 @@ def test_query_with_and_without_the_persistent_kernel(cuda):
             sum(v.mean() for v in out["rendered"].values()).backward()
             res.append((out, product_grads(model), model.accel.occ._occ_val_grid_pcl.clone()))
         finally:
-            GN.PERSISTENT_UPSAMPLE = True
+            GN.PERSISTENT_UPSAMPLE = "auto"
     (a, ga, pa), (b, gb, pb) = res
     for k in ("t", "opacity_alpha", "rgb", "nablas", "rays_inds_hit", "pack_infos_hit"):
         assert torch.equal(a["volume_buffer"][k], b["volume_buffer"][k]), k

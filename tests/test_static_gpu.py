@@ -158,26 +158,3 @@ def test_random_training_batch(cuda):
     for kk, v in g_ref.items():
         if v is not None:
             assert rel_l2(g[kk], v) <= 2e-5, (kk, rel_l2(g[kk], v))
-
-
-def test_capture_after_an_eager_backward_whose_graph_is_still_alive(cuda):
-    """a kept loss / rendered tensor of an earlier default-stream backward pins the parameters' AccumulateGrad nodes to the default stream;
-    the static step does not use them (autograd.grad + explicit accumulation), so the capture still works"""
-    from neuralsim_b200.graphics.neus_static import StaticFrame
-    _, model = make_pair(cuda)
-    model.train()
-    ro, rd = _rays(cuda, k=4)
-    ha = torch.zeros(ro.shape[0], 4, device=cuda)
-    kept, g_ref = _host_sized(model, ro, rd, ha)              # `kept` holds the graph on purpose
-    for p in model.parameters():
-        p.grad = torch.zeros_like(p)
-    frame = StaticFrame(model, ro.shape[0], loss_fn=_loss, near=0.01, zero_grads=True, slack=2.0)
-    frame.step(ro, rd, ha)
-    frame.step(ro, rd, ha)                                     # replay
-    assert frame.captures == 1 and frame.counts()["overflow"] == 0
-    for kk in KEYS:
-        assert torch.equal(frame.rendered[kk], kept["rendered"][kk]), kk
-    g = product_grads(model)
-    for kk, v in g_ref.items():
-        if v is not None:
-            assert rel_l2(g[kk], v) <= 2e-5, (kk, rel_l2(g[kk], v))
