@@ -23,12 +23,13 @@ __device__ __forceinline__ int64_t nwarps_() { return ((int64_t)gridDim.x * bloc
 // counts[N] (int32, >= 0)  ->  first[N] (exclusive prefix sum), and for the non-zero entries, in order:
 // nz_index[j] = i, nz_pack[j] = (first_i, counts_i) (int64), optionally gathered values nz_src[j] = src[i];
 // info2[N,2] = (first_i, counts_i) int32 (the reference's `packed_info`); totals = (sum, number of non-zeros).
-constexpr int kScanT = 1024, kScanI = 8, kScanMaxBlocks = 128;     // every block is resident (128 <= #SMs): spinning on predecessors is safe
+constexpr int kScanT = 1024, kScanI = 8, kScanMaxBlocks = 128;
 struct ScanWs {                                                      // zero-filled by the caller before every launch
     long long sum[kScanMaxBlocks];
     int nz[kScanMaxBlocks];
     int flag[kScanMaxBlocks];
-};
+    int ticket;                                                      // segments are handed out in the order the blocks START: a block only waits for
+};                                                                   // blocks that are already running (no co-residency assumption, no deadlock)
 
 __device__ __forceinline__ void block_scan_pair(int64_t &ps, int32_t &pz, int lane, int warp, int64_t *s_sum, int32_t *s_nz) {
 #pragma unroll
@@ -65,7 +66,10 @@ k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int64_t seg, ScanWs
     __shared__ int32_t s_nz[32];
     __shared__ int64_t s_carry_sum;
     __shared__ int32_t s_carry_nz;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    __shared__ int s_b;
+    if (threadIdx.x == 0) s_b = atomicAdd(&ws->ticket, 1);
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = s_b;
     const int64_t lo = (int64_t)b * seg, hi = min(n, lo + seg);
     // ---- (1) totals of my segment
     int64_t ps = 0;

@@ -208,3 +208,110 @@ class OccGridAccel(nn.Module):
 
     def ray_march(self, rays_o, rays_d, near=None, far=None, perturb=False, **march_cfg):
         return occgrid_raymarch(self.occ.occ_grid, rays_o, rays_d, near, far, perturb=perturb, **march_cfg)
+
+
+# ---------------------------------------------------------------------------------------------------------------- batched (multi-object)
+class OccGridEmaBatched(nn.Module):
+    """`num_batches` occupancy grids of one resolution, one per object instance of a shared model (occgrid/ema_batched.py:17-309):
+    `occ_val_grid` [B,X,Y,Z] with the EMA / per-voxel-maximum update of `update_batched_occ_val_grid_idx_` (occgrid/utils.py:111-124)."""
+
+    def __init__(self, num_batches, resolution=(32, 32, 32), occ_val_fn_cfg=dict(type="sdf", inv_s=256.0), occ_thre=0.3, ema_decay=0.95,
+                 update_from_samples_cfg=dict(), dtype=torch.float, device=None):
+        super().__init__()
+        res = torch.tensor([resolution] * 3 if isinstance(resolution, int) else list(resolution), dtype=torch.int32, device=device)
+        self.num_batches = int(num_batches)
+        self.register_buffer("resolution", res, persistent=False)
+        shape = [self.num_batches] + res.tolist()
+        self.register_buffer("occ_grid", torch.zeros(shape, dtype=torch.bool, device=device), persistent=True)
+        self.register_buffer("occ_val_grid", torch.zeros(shape, dtype=dtype, device=device), persistent=True)
+        if occ_val_fn_cfg.get("type", "sdf") != "sdf":
+            raise RuntimeError("only occ_val_fn type 'sdf' is built")
+        self.occ_inv_s, self.occ_thre, self.ema_decay = float(occ_val_fn_cfg["inv_s"]), occ_thre, ema_decay
+        self.should_collect_samples = update_from_samples_cfg is not None
+        if self.should_collect_samples:
+            self.register_buffer("_occ_val_grid_pcl", torch.zeros(shape, dtype=dtype, device=device), persistent=False)
+
+    def occ_val_fn(self, sdf):
+        return sdf_to_occ_val(sdf.half(), self.occ_inv_s).float()
+
+    def _gidx_of(self, pts):
+        return ((pts / 2. + 0.5) * self.resolution).long().clamp(self.resolution.new_tensor([0]), self.resolution - 1)
+
+    def _ravel(self, bidx, gidx):
+        r = self.occ_val_grid.shape[1:]
+        return bidx * (r[0] * r[1] * r[2]) + (gidx * gidx.new_tensor([r[1] * r[2], r[2], 1])).sum(-1)
+
+    @torch.no_grad()
+    def update(self, pts, bidx, val):
+        """`_step_update_occ` with per-point batch indices (ema_batched.py:226-261): evidence of the points + the collected evidence -> decay and
+        per-voxel maximum on the touched voxels of the touched grids -> threshold"""
+        bidx, occ_val = bidx.flatten().long(), self.occ_val_fn(val.flatten())
+        gidx = self._gidx_of(pts.flatten(0, -2))
+        if self.should_collect_samples:
+            idx = self._occ_val_grid_pcl.nonzero().long()
+            if idx.numel() > 0:
+                bidx = torch.cat([bidx, idx[:, 0]], 0)
+                gidx = torch.cat([gidx, idx[:, 1:]], 0)
+                occ_val = torch.cat([occ_val, self._occ_val_grid_pcl[tuple(idx.t())]], 0)
+            self._occ_val_grid_pcl.zero_()
+        flat = self._ravel(bidx, gidx)
+        new = (self.ema_decay * self.occ_val_grid.flatten()).scatter_reduce_(0, flat, occ_val.to(self.occ_val_grid), "amax", include_self=True)
+        self.occ_val_grid.view(-1)[flat] = new[flat]
+        self.occ_grid = self.occ_val_grid > self.occ_thre
+
+    @torch.no_grad()
+    def collect_samples(self, pts, bidx, val):
+        if self.training and self.should_collect_samples:
+            flat = self._ravel(bidx.flatten().long(), self._gidx_of(pts.flatten(0, -2)))
+            self._occ_val_grid_pcl.view(-1).scatter_reduce_(0, flat, self.occ_val_fn(val.flatten()).to(self._occ_val_grid_pcl), "amax", include_self=True)
+
+
+class OccGridAccelBatched(nn.Module):
+    """The accel of a shared (batched) model: the grids of the instances of the CURRENT batch are selected with `set_condition`, rays carry the
+    batch index of their object and are marched by the batched kernel (occgrid_accel/batched.py:31-170; csrc/march.cu with `batch_inds`)."""
+
+    def __init__(self, num_batches, device=None, **occ_cfg):
+        super().__init__()
+        occ_cfg.pop("type", None)
+        self.occ = OccGridEmaBatched(num_batches, **occ_cfg, device=device)
+        self.training_granularity = 0.0
+        self.clean_condition()
+
+    def set_condition(self, batch_size, *, ins_inds_per_batch):
+        self.batch_size, self.ins_inds_per_batch = int(batch_size), ins_inds_per_batch
+        self.occ_grid_per_batch = self.occ.occ_grid[ins_inds_per_batch].contiguous()
+
+    def clean_condition(self):
+        self.batch_size = self.ins_inds_per_batch = self.occ_grid_per_batch = None
+
+    def _need(self):
+        if self.occ_grid_per_batch is None:
+            raise RuntimeError("OccGridAccelBatched: call set_condition() first")
+
+    @torch.no_grad()
+    def cur_batch__query_occupancy(self, pts, bidx):
+        self._need()
+        g = self.occ._gidx_of(pts)
+        return self.occ_grid_per_batch[(bidx,) + tuple(g.movedim(-1, 0))]
+
+    @torch.no_grad()
+    def cur_batch__sample_pts_in_occupied(self, num_pts):
+        self._need()
+        idx = self.occ_grid_per_batch.nonzero().long()
+        assert idx.numel() > 0, "Occupancy grid becomes empty during training."
+        pts, vidx = sample_pts_in_voxels(idx[:, 1:], num_pts, self.occ.resolution, self.occ.occ_val_grid.dtype)
+        return pts, idx[:, 0][vidx]
+
+    def cur_batch__ray_march(self, rays_o, rays_d, rays_bidx=None, *, near=None, far=None, perturb=False, step_size=1e-3, max_step_size=1e10,
+                             dt_gamma=0.0, max_steps=512):
+        from ..graphics.raymarch import occgrid_raymarch_batched
+        self._need()
+        return occgrid_raymarch_batched(self.occ_grid_per_batch, rays_o, rays_d, near, far, rays_bidx, perturb=perturb, step_size=step_size,
+                                        max_step_size=max_step_size, dt_gamma=dt_gamma, max_steps=max_steps)
+
+    def cur_batch__collect_samples(self, pts, bidx, val):
+        self.occ.collect_samples(pts, self.ins_inds_per_batch[bidx], val)
+
+    def cur_batch__step(self, pts, bidx, val):
+        """EMA update with points of the current batch (bidx = batch-local instance index)"""
+        self.occ.update(pts, self.ins_inds_per_batch[bidx], val)

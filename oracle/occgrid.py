@@ -59,3 +59,13 @@ def step_update_occ(occ_val_grid, pts, sdf, *, inv_s, ema_decay, occ_thre, pcl=N
         pcl[...] = 0
     update_occ_val_grid_idx(occ_val_grid, gidx, occ_val, ema_decay)
     return occ_val_grid, binarize(occ_val_grid, occ_thre), pcl
+
+
+def update_batched_occ_val_grid_idx(grid, bidx, gidx, occ_val, ema_decay=1.0):
+    """utils.py:111-120 (per-point batch indices): the same update on a [B,X,Y,Z] grid, raveled with the batch index in front.  In place."""
+    shape = grid.shape[1:]
+    flat = np.asarray(bidx, dtype=np.int64) * int(np.prod(shape)) + (gidx * np.array([shape[1] * shape[2], shape[2], 1], dtype=np.int64)).sum(-1)
+    new = (np.float32(ema_decay) * grid.reshape(-1).astype(np.float32)).astype(np.float32)
+    np.maximum.at(new, flat, np.asarray(occ_val, dtype=np.float32).reshape(-1))
+    grid.reshape(-1)[flat] = new[flat]
+    return grid

@@ -80,3 +80,39 @@ def test_step_uses_the_device_update_and_matches_the_torch_chain(cuda):
         finally:
             A.DEVICE_EMA = True
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_batched_update_equals_oracle():
+    """OccGridEmaBatched.update (CPU torch chain) == the oracle's restatement of update_batched_occ_val_grid_idx_"""
+    from neuralsim_b200.fields.accel import OccGridEmaBatched
+    rng = np.random.default_rng(3)
+    B, res, n = 4, (10, 8, 12), 6000
+    pts = rng.uniform(-1.02, 1.02, (n, 3)).astype(np.float32)
+    bidx = rng.integers(0, B - 1, n)                               # grid B-1 stays untouched
+    sdf = (np.linalg.norm(pts, axis=-1) - 0.5).astype(np.float16).astype(np.float32) * 0.05
+    grid = rng.uniform(0, 1, (B,) + res).astype(np.float32)
+    occ = OccGridEmaBatched(B, resolution=list(res), update_from_samples_cfg=None)
+    occ.occ_val_grid = torch.from_numpy(grid.copy())
+    occ.update(torch.from_numpy(pts), torch.from_numpy(bidx), torch.from_numpy(sdf))
+    ref = og.update_batched_occ_val_grid_idx(grid.copy(), bidx, og.voxel_index(pts, res), og.normalized_logistic_density_half(sdf, 256.0).astype(np.float32), 0.95)
+    assert np.array_equal(occ.occ_val_grid.numpy(), ref)
+    assert np.array_equal(occ.occ_val_grid.numpy()[B - 1], grid[B - 1])
+    assert np.array_equal(occ.occ_grid.numpy(), ref > np.float32(0.3))
+
+
+@pytest.mark.gpu
+def test_batched_accel_marches_the_conditioned_grids(cuda):
+    """set_condition selects the instances' grids; rays carry the batch index; an empty grid yields no sample, a full one marches the box"""
+    from neuralsim_b200.fields.accel import OccGridAccelBatched
+    acc = OccGridAccelBatched(6, resolution=[16, 16, 16], device=cuda)
+    acc.occ.occ_grid[4] = True                                      # instance 4: everything occupied; instance 2: nothing
+    acc.set_condition(2, ins_inds_per_batch=torch.tensor([4, 2], device=cuda))
+    o = torch.tensor([[0., 0., -3.]] * 4, device=cuda)
+    d = torch.tensor([[0., 0., 1.]] * 4, device=cuda)
+    bidx = torch.tensor([0, 1, 0, 1], device=cuda)
+    ret = acc.cur_batch__ray_march(o, d, bidx, near=torch.full([4], 2.0, device=cuda), far=torch.full([4], 4.0, device=cuda), step_size=0.1, max_steps=64)
+    assert ret.ridx_hit.tolist() == [0, 2] and ret.pack_infos[:, 1].tolist() == [20, 20]
+    assert bool((ret.bidx == 0).all())
+    assert acc.cur_batch__query_occupancy(torch.zeros(2, 3, device=cuda), torch.tensor([0, 1], device=cuda)).tolist() == [True, False]
+    pts, b = acc.cur_batch__sample_pts_in_occupied(100)
+    assert bool((b == 0).all()) and pts.shape[0] >= 100
