@@ -189,14 +189,14 @@ def _query_fused_tail(model, ray_tested, view_dirs, rays_h_appear, rays_o, rays_
 
 
 def _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_appear, ridx_all, depths, *, nablas_has_grad,
-                      with_rgb, with_normal, dtype):
-    if view_dirs is None and not with_rgb and with_normal and FUSED_STAGES and getattr(model, "use_view_dirs", False) and not rays_d.requires_grad:
+                      with_rgb, with_normal, dtype, cond_kw=None):
+    if view_dirs is None and cond_kw is None and not with_rgb and with_normal and FUSED_STAGES and getattr(model, "use_view_dirs", False) and not rays_d.requires_grad:
         # LiDAR-style rays (with_rgb=False, with_normal=True: code_single/tools/train.py:900): sdf + second-order nablas are what is needed; the
         # fused op computes them (its radiance head runs too and is dropped; no gradient reaches the radiance net)
         view_dirs = rays_d / rays_d.detach().norm(dim=-1).clamp_min(1.0e-10).unsqueeze(-1)
         if rays_h_appear is None and getattr(model, "use_h_appear", False):
             rays_h_appear = rays_d.new_zeros(rays_d.shape[0], model.radiance_net.blocks.layers[0].in_features - 54)
-    if (FUSED_STAGES and (with_rgb or with_normal) and view_dirs is not None and getattr(model, "_color_fusable", lambda: False)()
+    if (FUSED_STAGES and cond_kw is None and (with_rgb or with_normal) and view_dirs is not None and getattr(model, "_color_fusable", lambda: False)()
             and not (rays_h_appear is not None and rays_h_appear.requires_grad) and not depths.requires_grad
             # learnable rays (pose refinement): the reference's model.forward(x = o + d t) carries d(loss)/d(rays); the fused op detaches them
             and not (rays_o.requires_grad or rays_d.requires_grad or view_dirs.requires_grad)):
@@ -212,6 +212,8 @@ def _net_forward_into(volume_buffer, model, rays_o, rays_d, view_dirs, rays_h_ap
         kw["h_appear"] = rays_h_appear[ridx_all]
     if view_dirs is not None:
         kw["v"] = view_dirs[ridx_all]
+    if cond_kw is not None:
+        kw.update(cond_kw(ridx_all))
     out = model.forward(**kw)
     volume_buffer["net_x"] = x
     if "nablas" in out:
@@ -249,7 +251,19 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
     dir_scale = rays_d.detach().norm(dim=-1)
     view_dirs = rays_d / dir_scale.clamp_min(1.0e-10).unsqueeze(-1) if use_view_dirs else None
 
-    if (FUSED_STAGES and num_coarse > 0 and rays_o.is_cuda and dtype == torch.float32 and hasattr(model, "forward_sdf_on_rays")
+    # conditioned field families (dynamic / generative models) take per-ray ts / fidx / bidx / pix with every network query
+    # (neus_ray_query.py:776-790, 846-866); they run the op-by-op chain below, the values gathered per sample
+    cond = {k: ray_tested[f"rays_{k}"] for k in ("ts", "fidx", "bidx", "pix") if getattr(model, f"use_{k}", False) and ray_tested.get(f"rays_{k}") is not None}
+    cond_kw = (lambda ridx_: {k: v[ridx_] for k, v in cond.items()}) if cond else (lambda ridx_: {})
+
+    def sdf_on_rays(ridx_, t_):
+        if not cond:
+            return model.forward_sdf_on_rays(ridx_, t_, rays_o, rays_d)["sdf"]
+        r2 = ridx_.unsqueeze(-1).expand(t_.shape) if t_.dim() == 2 else ridx_
+        x_ = torch.addcmul(rays_o[r2], rays_d[r2], t_.unsqueeze(-1))
+        return model.forward_sdf(x_.flatten(0, -2), **cond_kw(r2.reshape(-1)))["sdf"].view(t_.shape)
+
+    if (FUSED_STAGES and not cond and num_coarse > 0 and rays_o.is_cuda and dtype == torch.float32 and hasattr(model, "forward_sdf_on_rays")
             and getattr(getattr(model.accel, "occ", None), "occ_grid", None) is not None and model.accel.occ.occ_grid.dim() == 3
             and not (rays_o.requires_grad or rays_d.requires_grad or near.requires_grad or far.requires_grad)
             and set(march_cfg) <= {"step_size", "max_steps", "max_step_size", "dt_gamma", "step_size_factor"}):
@@ -262,7 +276,7 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
     if num_coarse > 0:
         depths_coarse_1, deltas_coarse_1 = batch_sample_step_linear(near, far, num_coarse + 1, perturb=perturb, return_dt=True)
     marched = model.accel.ray_march(rays_o, rays_d, near=near, far=far, perturb=perturb, **march_cfg)
-    net_kw = dict(nablas_has_grad=nablas_has_grad, with_rgb=with_rgb, with_normal=with_normal, dtype=dtype)
+    net_kw = dict(nablas_has_grad=nablas_has_grad, with_rgb=with_rgb, with_normal=with_normal, dtype=dtype, cond_kw=cond_kw if cond else None)
 
     if marched.ridx_hit is not None:
         # ---------------- up-sample on the marched samples (no grad)
@@ -271,7 +285,7 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
         n_hit = marched.num_hit_rays
         rays_inds_hit = rays_inds[marched.ridx_hit]
         with torch.no_grad():
-            sdf = model.forward_sdf(marched.samples)["sdf"].to(dtype)
+            sdf = model.forward_sdf(marched.samples, **cond_kw(marched.ridx))["sdf"].to(dtype)
             fine_stages = []
             for i, factor in enumerate(upsample_inv_s_factors):
                 if FUSED_STAGES:
@@ -298,7 +312,7 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
                     merged[pidx0], merged[pidx1] = depth_samples, fine.flatten()
                     depth_samples = merged
                     if i < n_stage - 1:
-                        sdf_fine = model.forward_sdf_on_rays(marched.ridx_hit, fine, rays_o, rays_d)["sdf"].to(dtype)
+                        sdf_fine = sdf_on_rays(marched.ridx_hit, fine).to(dtype)
                         sdf_new = sdf.new_empty([n_old + fine.numel()])
                         sdf_new[pidx0], sdf_new[pidx1] = sdf, sdf_fine.flatten()
                         sdf = sdf_new
@@ -307,7 +321,8 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
         # ---------------- boundary points with grad, alpha, compression
         if num_coarse == 0:
             x = torch.addcmul(rays_o[marched.ridx_hit].unsqueeze(-2), rays_d[marched.ridx_hit].unsqueeze(-2), depths_1.unsqueeze(-1))
-            alpha = neus_ray_sdf_to_alpha(model.forward_sdf(x.flatten(0, -2))["sdf"].to(dtype).view(depths_1.shape), forward_inv_s)
+            alpha = neus_ray_sdf_to_alpha(sdf_on_rays(marched.ridx_hit, depths_1).to(dtype) if cond else
+                                          model.forward_sdf(x.flatten(0, -2))["sdf"].to(dtype).view(depths_1.shape), forward_inv_s)
             depths = depths_1[..., :-1] + depths_1.diff(dim=-1) / 2.
             pack_infos = get_pack_infos_from_batch(n_hit, depths.size(-1), device=device)
             nidx_useful, pack_infos_useful, pidx_useful = packed_volume_render_compression(alpha.flatten(), pack_infos)
@@ -331,7 +346,7 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
         ridx_all[pidx0], ridx_all[pidx1] = ridx_coarse.unsqueeze(-1), marched.ridx_hit.unsqueeze(-1)
         depths_1_packed[pidx0], depths_1_packed[pidx1] = depths_coarse_1, depths_1
         depths_packed = depths_1_packed + packed_diff(depths_1_packed, pack_infos) / 2.
-        sdf_b = model.forward_sdf_on_rays(ridx_all, depths_1_packed, rays_o, rays_d)["sdf"].to(dtype)
+        sdf_b = sdf_on_rays(ridx_all, depths_1_packed).to(dtype)
         if FUSED_STAGES:
             alpha_packed, nidx_useful, pack_infos_useful, pidx_useful = neus_fused.neus_alpha_compress(sdf_b, forward_inv_s, pack_infos)
         else:
@@ -352,7 +367,7 @@ def neus_ray_query_march_occ_multi_upsample_compressed(
     if num_coarse == 0:
         return empty, {}
     x = torch.addcmul(rays_o.unsqueeze(-2), rays_d.unsqueeze(-2), depths_coarse_1.unsqueeze(-1))
-    sdf_c = model.forward_sdf(x.flatten(0, -2))["sdf"].to(dtype).view(depths_coarse_1.shape)
+    sdf_c = (sdf_on_rays(torch.arange(R, device=device), depths_coarse_1) if cond else model.forward_sdf(x.flatten(0, -2))["sdf"].view(depths_coarse_1.shape)).to(dtype)
     alpha_coarse = neus_ray_sdf_to_alpha(sdf_c, forward_inv_s)
     depths_coarse = depths_coarse_1[..., :num_coarse] + deltas_coarse_1[..., :num_coarse] / 2.
     pack_infos_coarse = get_pack_infos_from_batch(R, num_coarse, device=device)

@@ -147,3 +147,48 @@ def test_render_fused_equals_unfused_chain(perturb, stages):
     for k, g in outs[True][1].items():
         if g is not None:
             assert rel_l2(g, outs[False][1][k]) < 2e-3, k
+
+
+def test_conditioned_query_kwargs_reach_every_network_call(cuda):
+    """rays_ts / rays_fidx of `ray_tested` (neus_ray_query.py:776-790, 846-866): a model that declares `use_ts` / `use_fidx` receives, with EVERY
+    sdf / colour query, the value of the ray each sample belongs to; the result equals the unconditioned query (the stand-in ignores the values)"""
+    from oracle import scene as oscene
+    from util import make_pair
+    import neuralsim_b200.graphics.neus as N
+    _, model = make_pair(cuda)
+    ro, rd = oscene.pinhole_rays(20, 24, oscene.orbit_camera(1, 8))
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    n = ro.shape[0]
+    ts = torch.arange(n, device=cuda, dtype=torch.float32) * 0.5
+    fidx = torch.arange(n, device=cuda) % 7
+    rt0 = model.ray_test(ro, rd, near=0.01, rays_h_appear=torch.zeros(n, 4, device=cuda))
+    rt = model.ray_test(ro, rd, near=0.01, rays_h_appear=torch.zeros(n, 4, device=cuda), rays_ts=ts, rays_fidx=fidx)
+    assert torch.equal(rt["rays_ts"], ts[rt["rays_inds"]])
+    qp = dict(model.ray_query_cfg["query_param"])
+    model.eval()
+    with torch.no_grad():
+        want, _ = N.neus_ray_query_march_occ_multi_upsample_compressed(model, rt0, **qp)
+    seen = []
+
+    class Conditioned:
+        use_ts, use_fidx = True, True
+
+        def __getattr__(self, k):
+            return getattr(model, k)
+
+        def forward_sdf(self, x, ts=None, fidx=None, **kw):
+            assert ts is not None and fidx is not None and ts.shape[0] == x.reshape(-1, 3).shape[0] == fidx.shape[0]
+            assert torch.equal((ts * 2).round().long() % 7, fidx)          # both belong to the same ray
+            seen.append(ts.shape[0])
+            return model.forward_sdf(x, **kw)
+
+        def forward(self, x, ts=None, fidx=None, **kw):
+            assert ts is not None and ts.shape[0] == x.shape[0] and torch.equal((ts * 2).round().long() % 7, fidx)
+            seen.append(-x.shape[0])
+            return model.forward(x, **kw)
+
+    with torch.no_grad():
+        got, _ = N.neus_ray_query_march_occ_multi_upsample_compressed(Conditioned(), rt, **qp)
+    assert len([s for s in seen if s > 0]) >= 4 and len([s for s in seen if s < 0]) == 1       # marched + 2 fine stages + boundary; one colour query
+    assert torch.equal(got["rays_inds_hit"], want["rays_inds_hit"]) and torch.equal(got["pack_infos_hit"], want["pack_infos_hit"])
+    assert torch.allclose(got["t"], want["t"]) and torch.allclose(got["rgb"], want["rgb"], atol=2e-3) and torch.allclose(got["opacity_alpha"], want["opacity_alpha"], atol=2e-3)
