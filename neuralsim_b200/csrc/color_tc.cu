@@ -122,6 +122,10 @@ __device__ __forceinline__ void load_point_net(const PointSrc &ps, int64_t i, bo
     for (int d = 0; d < 3; ++d) xs[d] = fminf(fmaxf(__fmaf_rn(xn[d], 0.5f, 0.5f), 1.0e-6f), 1.f - 1.0e-6f);
 }
 
+// The colour kernels run at 2-3 CTAs per SM (TMEM / shared-memory bound), i.e. 8-12 warps: their gathers live on loads in flight PER THREAD, and
+// registers are plentiful -> four levels (32 corner loads) per gather trip instead of the two of k_fused_sdf_tc (which runs 24 warps per SM).
+constexpr int kColorGatherU = 4;
+
 // ===================================================================================================================== forward
 __global__ void __launch_bounds__(kTile)
 k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev net, const PointSrc ps, const float *__restrict__ view_dirs,
@@ -190,7 +194,7 @@ k_color_fwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev n
         float xn[3], xs[3];
         int64_t ray;
         load_point_net(ps, i, valid, xn, xs, ray);
-        gather_row_to_tile<kTile>(m, grid, xs, max_level, sX, tid);          // h -> chunks 0..3 of X
+        gather_row_to_tile<kTile, kColorGatherU>(m, grid, xs, max_level, sX, tid);          // h -> chunks 0..3 of X
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -664,8 +668,8 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
             *reinterpret_cast<uint4 *>(sT + kTileBytes + c * kChunk + tid * 16) = tc::pack8_f16(uu);
         }
         // dg = J gin (fp16), level by level, into my row of Ge
-#pragma unroll 2
-        for (uint32_t p = 0; p < 16; ++p) {               // two levels per trip: 16 independent corner loads in flight
+#pragma unroll 4
+        for (uint32_t p = 0; p < 16; ++p) {               // four levels per trip: 32 independent corner loads in flight (2 CTAs / SM: registers are free)
             uint32_t packed = 0;
             if ((int)m.level[p] <= max_level) {
                 float J0[3], J1[3];

@@ -10,8 +10,10 @@ from util import make_pair, product_grads, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-4
-GRAD_TOL_DEFAULT = 2e-2
-GRAD_TOL = {}            # per-tensor overrides (set from the measured errors)
+# measured on the B200 (profiles/r02_grad_parity_errors.json): grid 1.3e-3, dec_W1 2.7e-3, ln_inv_s 1.0e-3, every other tensor 1.7e-4 .. 6.1e-4
+# (round 1 accepted 2e-2 for all of them); bounds = ~3 x measured
+GRAD_TOL_DEFAULT = 2e-3
+GRAD_TOL = dict(grid=4e-3, dec_W1=8e-3, ln_inv_s=3e-3)
 
 
 def _rays(H=30, W=40, k=1):
