@@ -61,6 +61,14 @@ class OccGridEma(nn.Module):
         # the model's sdf is fp16-valued (autocast decoder): evaluate like the reference does on its half tensor, then widen
         return sdf_to_occ_val(sdf.half(), self.occ_inv_s).float()
 
+    def _set_grid(self, new):
+        """the reference re-assigns `self.occ_grid = binarize(...)` (ema_single.py:190); here the buffer is updated IN PLACE when the shape is
+        unchanged, so that raw pointers captured by a CUDA graph (graphics/neus_static.py) keep seeing the current grid"""
+        if new.shape == self.occ_grid.shape and new.device == self.occ_grid.device:
+            self.occ_grid.copy_(new)
+        else:
+            self.occ_grid = new
+
     def collect_struct(self):
         """nsb_occ_collect for the fused query kernels (None when samples are not collected): they max-accumulate the occupancy evidence
         of every point they evaluate into `_occ_val_grid_pcl`, which is what `collect_samples(x, sdf)` does after the query."""
@@ -85,7 +93,7 @@ class OccGridEma(nn.Module):
         flat = self._ravel(gidx)
         new = (ema_decay * self.occ_val_grid.flatten()).scatter_reduce_(0, flat, occ_val.flatten().to(self.occ_val_grid), "amax", include_self=True)
         self.occ_val_grid.view(-1)[flat] = new[flat]
-        self.occ_grid = self.occ_val_grid > self.occ_thre
+        self._set_grid(self.occ_val_grid > self.occ_thre)
 
     @torch.no_grad()
     def _step_update_device(self, pts, sdf):
@@ -105,11 +113,11 @@ class OccGridEma(nn.Module):
                                            None, L.c_f32(self.ema_decay), L.c_f32(self.occ_thre), L.ptr(scratch), L.stream_ptr()), "occ_ema_update")
         if grid is not self.occ_val_grid:
             self.occ_val_grid.copy_(grid)
-        self.occ_grid = occ
+        self._set_grid(occ)
 
     @torch.no_grad()
     def set_occ_grid(self, occ_grid):
-        self.occ_grid = occ_grid.to(self.occ_grid.device).bool().contiguous()
+        self._set_grid(occ_grid.to(self.occ_grid.device).bool().contiguous())
         self.occ_val_grid = self.occ_grid.to(self.occ_val_grid.dtype)
         self.is_initialized.fill_(True)
 
@@ -121,7 +129,7 @@ class OccGridEma(nn.Module):
         mode = cfg.pop("mode")
         if mode == "constant":
             self.occ_val_grid.fill_(cfg["constant_value"])
-            self.occ_grid = self.occ_val_grid > self.occ_thre
+            self._set_grid(self.occ_val_grid > self.occ_thre)
         elif mode == "from_net":
             for _ in range(cfg.get("num_steps", 4)):
                 empty = self.occ_grid.logical_not().nonzero().long()

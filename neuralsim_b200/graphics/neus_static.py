@@ -515,7 +515,7 @@ class StaticFrame:
         na = h_appear_dim if h_appear_dim is not None else (model.radiance_net.blocks.layers[0].in_features - 54 if model.use_h_appear else 0)
         self.h_appear = torch.zeros(self.n_rays, na, device=dev) if na > 0 else None
         self.cnt = torch.zeros(32, dtype=torch.int64, device=dev)
-        self.graph, self.loss, self.rendered, self.buffers = None, None, None, None
+        self.graph, self.loss, self.rendered, self.buffers, self._occ_captured = None, None, None, None, None
         self.captures = 0
 
     # -- sizes
@@ -587,6 +587,7 @@ class StaticFrame:
             # capture on the warm-up's stream: the parameters' AccumulateGrad nodes were created there.  (A backward that ran on the default
             # stream BEFORE this and whose graph is still referenced -- a kept loss / rendered tensor -- pins those nodes to the default
             # stream and invalidates the capture: drop such references first.)
+            self._occ_captured = self.model.accel.occ.occ_grid
             with torch.cuda.graph(g, stream=side):
                 self.rendered, self.buffers, self.loss = self._run()
             self.graph = g
@@ -604,6 +605,10 @@ class StaticFrame:
         if self.graph is None and (self.use_graph or self.march_cap is None):
             self.capture()
         if self.graph is not None:
+            occ = self.model.accel.occ.occ_grid
+            if self._occ_captured is not None and occ.data_ptr() != self._occ_captured.data_ptr():
+                # somebody RE-ASSIGNED the grid (the reference's EMA does, ema_single.py:190): the graph reads the tensor it captured -> refresh it
+                self._occ_captured.copy_(occ)
             self.graph.replay()
         else:
             self.rendered, self.buffers, self.loss = self._run()

@@ -158,3 +158,28 @@ def test_random_training_batch(cuda):
     for kk, v in g_ref.items():
         if v is not None:
             assert rel_l2(g[kk], v) <= 2e-5, (kk, rel_l2(g[kk], v))
+
+
+def test_graph_follows_parameter_and_occupancy_updates(cuda):
+    """between replays the optimiser changes the parameters in place and the EMA changes the occupancy grid (in place here, re-assigned by the
+    reference's own EMA code): the replayed graph must render what an eager run of the UPDATED model renders"""
+    from neuralsim_b200.graphics.neus_static import StaticFrame, render_static
+    _, model = make_pair(cuda)
+    model.train()
+    ro, rd = _rays(cuda, k=2)
+    ha = torch.zeros(ro.shape[0], 4, device=cuda)
+    frame = StaticFrame(model, ro.shape[0], near=0.01, slack=3.0)
+    with torch.no_grad():
+        frame.step(ro, rd, ha)
+        before = frame.rendered["rgb_volume"].clone()
+        model.radiance_net.blocks.layers[2].bias.add_(0.3)                      # an optimiser step (in place)
+        model.implicit_surface.encoding.flattened_params.mul_(1.01)
+        g = model.accel.occ.occ_grid.clone()
+        g[:, :, :32] = False                                                    # the EMA carved half of the grid away ...
+        model.accel.occ.occ_grid = g                                            # ... and RE-ASSIGNED the buffer, as the reference does
+        frame.step(ro, rd, ha)
+        want, _, _ = render_static(model, ro, rd, ha, near=0.01, march_cap=frame.march_cap, kept_cap=frame.kept_cap, coherent=frame.coherent)
+        assert frame.captures == 1 and frame.counts()["overflow"] == 0
+        assert not torch.equal(frame.rendered["rgb_volume"], before)
+        for kk in KEYS:
+            assert torch.equal(frame.rendered[kk], want[kk]), kk
