@@ -397,8 +397,13 @@ class VarSingleMixLinear(nn.Module):
     def set_iter(self, it):
         self.it = it
 
+    def mix_weight(self) -> float:
+        return min(max((self.it - self.start_it) / max(self.stop_it - self.start_it, 1), 0.), 1.)
+
     def forward(self, it: int = None):
         if it is not None:
             self.set_iter(it)
-        w = min(max((self.it - self.start_it) / max(self.stop_it - self.start_it, 1), 0.), 1.)
+        # the annealing weight is a host number in the reference; a captured CUDA graph would freeze it, so the static step
+        # (graphics/neus_static.py) reads it from a device scalar that it refreshes before every replay
+        w = self._w_dev if getattr(self, "_use_w_dev", False) else self.mix_weight()
         return (1 - w) * torch.exp(self.ln_inv_s * self.ln_inv_s_factor) + w * self.final_inv_s

@@ -554,8 +554,17 @@ class StaticFrame:
             for p in self.model.parameters():
                 if p.grad is not None:
                     p.grad.zero_()
-        rendered, _, buffers = render_static(self.model, self.rays_o, self.rays_d, self.h_appear, near=self.near, far=self.far, march_cap=self.march_cap,
-                                             kept_cap=self.kept_cap, coherent=bool(self.coherent), with_rgb=self.with_rgb, with_normal=self.with_normal, cnt=self.cnt)
+        cv = getattr(self.model, "ctrl_var", None)
+        if cv is not None and hasattr(cv, "mix_weight"):
+            if getattr(cv, "_w_dev", None) is None:
+                cv._w_dev = torch.zeros((), device=self.device)
+            cv._use_w_dev = True                             # inv_s annealing weight from a device scalar (refreshed in step())
+        try:
+            rendered, _, buffers = render_static(self.model, self.rays_o, self.rays_d, self.h_appear, near=self.near, far=self.far, march_cap=self.march_cap,
+                                                 kept_cap=self.kept_cap, coherent=bool(self.coherent), with_rgb=self.with_rgb, with_normal=self.with_normal, cnt=self.cnt)
+        finally:
+            if cv is not None:
+                cv._use_w_dev = False
         loss = None
         if self.loss_fn is not None:
             loss = self.loss_fn(rendered)
@@ -602,6 +611,11 @@ class StaticFrame:
         self.rays_d.copy_(rays_d, non_blocking=True)
         if self.h_appear is not None and rays_h_appear is not None:
             self.h_appear.copy_(rays_h_appear, non_blocking=True)
+        cv = getattr(self.model, "ctrl_var", None)
+        if cv is not None and hasattr(cv, "mix_weight"):
+            if getattr(cv, "_w_dev", None) is None:
+                cv._w_dev = torch.zeros((), device=self.device)
+            cv._w_dev.fill_(cv.mix_weight())                  # the variance schedule's host-side weight of THIS iteration
         if self.graph is None and (self.use_graph or self.march_cap is None):
             self.capture()
         if self.graph is not None:
