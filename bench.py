@@ -378,6 +378,112 @@ def run_cfg3(args, rank, world, local, device):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- cfg4 arm
+def run_cfg4(args, rank, world, local, device):
+    """BASELINE.json configs[3], the part of it that is built: N single-object NeuS models in one scene (8 instances of the cfg-2 object at
+    different poses / scales in front of one camera), every object queried in its own frame (fused host-sized path), the buffers collected, sorted per
+    ray and integrated jointly (neuralsim_b200/compose.py; reference app/renderers/buffer_compose_renderer.py:644-714), fwd + bwd.  The shared
+    conditional (permutohedral) foreground models of code_multi are not built."""
+    import torch.distributed as dist
+    from neuralsim_b200 import _lib
+    from neuralsim_b200.compose import BufferComposeRenderer, ObjectPose
+    if args.impl == "reference-cuda" and not use_reference_cuda_kernels():
+        raise SystemExit("bench.py: oracle/_ref is not built")
+    model = build_model(device).train()
+    flat, params = flat_grad_views(model)
+    rng = np.random.default_rng(0)
+    n_obj = 8
+    poses = []
+    for i in range(n_obj):
+        ang = 2 * math.pi * i / n_obj
+        a = rng.uniform(0, 2 * math.pi)
+        R = np.array([[math.cos(a), -math.sin(a), 0.], [math.sin(a), math.cos(a), 0.], [0., 0., 1.]])
+        poses.append(ObjectPose(rotation=R, translation=[2.6 * math.cos(ang), 2.6 * math.sin(ang), 0.4 * math.sin(3 * ang)], scale=0.7 + 0.05 * i, device=device))
+    objects = [(model, p) for p in poses]
+    renderer = BufferComposeRenderer(dict(near=0.01)).train()
+    views = []
+    for k in range(N_VIEWS):
+        a = 2 * math.pi * (k * world + rank) / (N_VIEWS * world)
+        o, d = pinhole_rays(H, W, (9.0 * math.cos(a), 9.0 * math.sin(a), 3.0))
+        views.append((o.to(device), d.to(device), o.pin_memory(), d.pin_memory()))
+    n_rays = H * W
+    ha = torch.zeros(n_rays, 4, device=device)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    loss_host = torch.zeros((), pin_memory=True)
+    img_host = torch.zeros(n_rays, 3).pin_memory()
+
+    def step(o, d):
+        flat.zero_()
+        out = renderer.render(objects, o, d, ha)["rendered"]
+        loss = loss_of(out)
+        if loss.requires_grad:
+            loss.backward()
+        if world > 1:
+            dist.all_reduce(flat)
+        return loss.detach(), out
+
+    def timed(fn, k):
+        ts = []
+        for i in range(k):
+            flush_buf.fill_(i & 0xff)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(i); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return ts
+
+    def resident(i):
+        v = views[i % N_VIEWS]
+        step(v[0], v[1])
+
+    def e2e(i):
+        v = views[i % N_VIEWS]
+        loss, out = step(v[2].to(device, non_blocking=True), v[3].to(device, non_blocking=True))
+        img_host.copy_(out["rgb_volume"], non_blocking=True)
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(args.warmup):
+        resident(i)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    t_e2e = timed(e2e, args.steps)
+    t_res = timed(resident, args.steps)
+    launches = (_lib.launch_count() - l0) // (2 * args.steps)
+    st_res, st_e2e = stats_of(t_res), stats_of(t_e2e)
+    ms = torch.tensor([st_res["mean"], st_e2e["mean"], st_res["median"]], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+    tot = world * n_rays
+    line = {"metric": "Mrays/sec fwd+bwd", "value": tot / (float(ms[0]) * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(ms[0]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "median": {"ms_per_step": float(ms[2]), "value": tot / (float(ms[2]) * 1e-3) / 1e6},
+            "config": {"workload": "cfg4", "what": f"{n_obj} single-object NeuS models (the cfg-2 object at {n_obj} poses / scales) composed along the rays of one 800x600 "
+                       "frame: per-object fused query (host-sized path) -> collect -> per-ray sort -> joint integration; no shared conditional models",
+                       "rays_per_step_per_gpu": n_rays, "parallelism": f"dp{world}", "mode": "host"},
+            "e2e": {"value": tot / (float(ms[1]) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": float(ms[1]), "h2d_bytes_per_step": int(2 * n_rays * 12),
+                    "d2h_bytes_per_step": int(n_rays * 12 + 4)},
+            "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches),
+            "step_ms": {"resident": [round(x, 3) for x in t_res], "e2e": [round(x, 3) for x in t_e2e]}}
+    if args.impl == "reference-cuda":
+        line["impl"] = "reference-cuda"
+    elif world == 1 and not args.no_ref_cuda:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--workload", "cfg4", "--steps", "5", "--warmup", "2"],
+                               capture_output=True, text=True, timeout=900)
+            rl = json.loads(r.stdout.strip().splitlines()[-1])
+            line["reference_cuda"] = {"value": rl["value"], "ms_per_step": rl["ms_per_step"], "steps": rl["steps"]}
+            line["vs_reference_cuda"] = {"value_ratio": line["value"] / rl["value"]}
+        except Exception as ex:
+            line["reference_cuda"] = {"unavailable": repr(ex)[:300]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------- main arm
 def stats_of(ts):
     a = np.asarray(ts, dtype=np.float64)
@@ -394,7 +500,7 @@ def main():
                     help="graph: the whole fwd+bwd step is ONE CUDA-graph launch (sizes stay on the device; default).  static: the same step launched "
                          "kernel by kernel.  host: the host-sized path (three host reads per step; round-1 behaviour)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank renders its own 800x600 frame; strong: the ranks share ONE frame (480000 / N rays each)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--rayschunk", type=int, default=0, help="host mode only: rays per render call (0 = the whole batch in one call)")
     ap.add_argument("--rays", type=int, default=H * W, help="rays per step and GPU (default: the full 800x600 frame)")
     ap.add_argument("--random-rays", action="store_true", help="draw the --rays rays of every pose as random pixels (a training batch) instead of the first rows")
@@ -432,6 +538,9 @@ def main():
         mode = "host"
     if args.workload == "cfg3":
         run_cfg3(args, rank, world, local, device)
+        return
+    if args.workload == "cfg4":
+        run_cfg4(args, rank, world, local, device)
         return
     model = build_model(device, collect_samples=args.collect_samples).train()
     near = 0.01
