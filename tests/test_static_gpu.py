@@ -168,13 +168,14 @@ def test_graph_follows_parameter_and_occupancy_updates(cuda):
     model.train()
     ro, rd = _rays(cuda, k=2)
     ha = torch.zeros(ro.shape[0], 4, device=cuda)
+    model.ctrl_var.start_it, model.ctrl_var.stop_it, model.ctrl_var.final_inv_s = 0, 100, 400.0        # the schedule's constants (config)
+    model.ctrl_var.set_iter(0)
     frame = StaticFrame(model, ro.shape[0], near=0.01, slack=3.0)
     with torch.no_grad():
         frame.step(ro, rd, ha)
         before = frame.rendered["rgb_volume"].clone()
         model.radiance_net.blocks.layers[2].bias.add_(0.3)                      # an optimiser step (in place)
         model.implicit_surface.encoding.flattened_params.mul_(1.01)
-        model.ctrl_var.start_it, model.ctrl_var.stop_it, model.ctrl_var.final_inv_s = 0, 100, 400.0
         model.ctrl_var.set_iter(37)                                            # the variance schedule moved on (a HOST-side weight in the reference)
         g = model.accel.occ.occ_grid.clone()
         g[:, :, :32] = False                                                    # the EMA carved half of the grid away ...
