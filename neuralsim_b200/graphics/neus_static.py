@@ -46,9 +46,10 @@ def _call(fn, what, cnt, k0, k1, *args):
     L.check(rc, what)
 
 
-def _scan(counts, cnt, slot, *, first=None, info2=None, index=None, pack=None, src=None, nz_src=None):
+def _scan(counts, cnt, slot, *, first=None, info2=None, index=None, pack=None, src=None, nz_src=None, ws=None):
     """nsb_scan_counts with the totals left in cnt[slot], cnt[slot + 1] (no host hand-off)"""
-    ws = torch.zeros(NF._scan_ws_bytes(), dtype=torch.uint8, device=counts.device)
+    if ws is None:
+        ws = torch.zeros(NF._scan_ws_bytes(), dtype=torch.uint8, device=counts.device)
     P = L.ptr
     L.check(L.lib().nsb_scan_counts(P(counts, "i32"), L.c_i64(counts.shape[0]), P(first, allow_none=True), P(info2, allow_none=True),
                                     P(index, allow_none=True), P(pack, allow_none=True), P(src, "i64", allow_none=True), P(nz_src, allow_none=True),
@@ -105,7 +106,7 @@ class _StaticSDF(torch.autograd.Function):
         flag = torch.empty(n, dtype=torch.int32, device=dev)
         _call(L.lib().nsb_flag_nonzero, "flag_nonzero", cnt, CNT_SLOTS["boundary"], None, P(d_sdf, "f32"), L.c_i64(n), P(flag), L.stream_ptr())
         keep = torch.empty(n, dtype=torch.int64, device=dev)
-        _scan(flag, cnt, CNT_SLOTS["nonzero"], index=keep)
+        _scan(flag, cnt, CNT_SLOTS["nonzero"], index=keep, ws=st.ws[3])
         with L.KERNEL_TIMER.time("fused_sdf_bwd", n):
             _call(L.lib().nsb_fused_sdf_bwd_indexed, "fused_sdf_bwd", cnt, CNT_SLOTS["nonzero"], None,
                   st.meta.c_ref, P(st.grid16, "f16"), ctypes.byref(st.dec), None, P(st.rays_o, "f32"), P(st.rays_d, "f32"), P(ctx.ridx, "i64"),
@@ -265,7 +266,7 @@ class _StaticComposite(torch.autograd.Function):
 
 class _State:
     """what the kernels of one static step share"""
-    __slots__ = ("meta", "grid16", "dec", "net", "held", "rays_o", "rays_d", "ml", "collect", "cnt")
+    __slots__ = ("meta", "grid16", "dec", "net", "held", "rays_o", "rays_d", "ml", "collect", "cnt", "ws")
 
 
 def _fp16_images(model):
@@ -273,7 +274,11 @@ def _fp16_images(model):
     s, b = model.implicit_surface, model.radiance_net.blocks.layers
     d = s.decoder.layers
     ps = [s.encoding.flattened_params, d[0].weight, d[0].bias, d[1].weight, d[1].bias, b[0].weight, b[0].bias, b[1].weight, b[1].bias, b[2].weight, b[2].bias]
-    t = [p.detach().to(torch.half).contiguous() for p in ps]
+    # one multi-tensor cast for the ten small tensors (a launch each otherwise: at 4096 rays per step the step is launch-bound), one for the table
+    t = [torch.empty(p.shape, dtype=torch.half, device=p.device) for p in ps]
+    with torch.no_grad():
+        t[0].copy_(ps[0].detach())
+        torch._foreach_copy_(t[1:], [p.detach() for p in ps[1:]])
     dec = L.SdfDecoderC(t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), d[0].out_features, float(d[0].activation.beta))
     r3 = s.radius3d_original
     fk = (r3.data_ptr(), r3._version, float(s.sdf_scale))
@@ -326,6 +331,8 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
         cnt.zero_()
     st = _State()
     st.cnt = cnt
+    wsb = (NF._scan_ws_bytes() + 255) // 256 * 256
+    st.ws = torch.zeros(4, wsb, dtype=torch.uint8, device=dev)          # the zeroed workspaces of the step's four scans, one fill
     with torch.no_grad():
         t16, st.dec, st.net, masters = _fp16_images(model)
         st.held, st.grid16 = t16, t16[0]
@@ -345,13 +352,15 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
                                       ctypes.c_int(0 if far is None else 1), L.c_f32(0. if far is None else far), P(o_n), P(d_n), P(nr), P(fr), P(flag),
                                       _slot(cnt, CNT_SLOTS["pairs"]), L.stream_ptr()), "ray_test_aabb")
         rays_inds = torch.empty(R, dtype=torch.int64, device=dev)
-        _scan(flag, cnt, CNT_SLOTS["n_rays"], index=rays_inds)
-        o_c, d_c = torch.zeros(R, 3, device=dev), torch.zeros(R, 3, device=dev)
-        n_c, f_c = torch.zeros(R, device=dev), torch.zeros(R, device=dev)
+        _scan(flag, cnt, CNT_SLOTS["n_rays"], index=rays_inds, ws=st.ws[0])
         ha = rays_h_appear.detach().contiguous().float() if (rays_h_appear is not None and model.use_h_appear) else None
         if ha is None and model.use_h_appear:             # LiDAR-style rays carry no appearance code: the (dropped) radiance head reads zeros
             ha = torch.zeros(R, model.radiance_net.blocks.layers[0].in_features - 54, device=dev)
-        ha_c = torch.zeros(R, ha.shape[1], device=dev) if ha is not None else None
+        n_ha = ha.shape[1] if ha is not None else 0
+        rbuf = torch.zeros(R * (8 + n_ha), device=dev)     # the compacted rays in ONE zero-filled allocation (rows beyond the live count stay 0)
+        o_c, d_c = rbuf[:3 * R].view(R, 3), rbuf[3 * R:6 * R].view(R, 3)
+        n_c, f_c = rbuf[6 * R:7 * R], rbuf[7 * R:8 * R]
+        ha_c = rbuf[8 * R:].view(R, n_ha) if ha is not None else None
         _call(lib.nsb_gather_rays, "gather_rays", cnt, CNT_SLOTS["n_rays"], None, P(rays_inds, "i64"), L.c_i64(R), P(o_n), P(d_n), P(nr), P(fr), P(o_c), P(d_c),
               P(n_c), P(f_c), P(ha, allow_none=True), P(ha_c, allow_none=True), L.c_i32(0 if ha is None else ha.shape[1]), L.stream_ptr())
         st.rays_o, st.rays_d = o_c, d_c
@@ -374,7 +383,7 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
         info2 = torch.empty(R, 2, dtype=torch.int32, device=dev)
         ridx_hit = torch.empty(R, dtype=torch.int64, device=dev)
         pack_infos = torch.empty(R, 2, dtype=torch.int64, device=dev)
-        _scan(num_steps, cnt, CNT_SLOTS["marched_raw"], info2=info2, index=ridx_hit, pack=pack_infos)
+        _scan(num_steps, cnt, CNT_SLOTS["marched_raw"], info2=info2, index=ridx_hit, pack=pack_infos, ws=st.ws[1])
         _query_counts(cnt, 0, nc1, num_fine, march_cap, kept_cap)
         depth = torch.empty(march_cap, dtype=torch.float32, device=dev)
         ridx32 = torch.empty(march_cap, dtype=torch.int32, device=dev)
@@ -444,7 +453,7 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
         nidx = torch.empty(R, dtype=torch.int64, device=dev)
         pinfo_kept = torch.empty(R, 2, dtype=torch.int64, device=dev)
         rays_inds_hit = torch.empty(R, dtype=torch.int64, device=dev)
-        _scan(steps, cnt, CNT_SLOTS["kept_raw"], first=first, index=nidx, pack=pinfo_kept, src=rays_inds, nz_src=rays_inds_hit)
+        _scan(steps, cnt, CNT_SLOTS["kept_raw"], first=first, index=nidx, pack=pinfo_kept, src=rays_inds, nz_src=rays_inds_hit, ws=st.ws[2])
         _query_counts(cnt, 1, nc1, num_fine, march_cap, kept_cap)
         pidx, ridx_k = torch.empty(kept_cap, dtype=torch.int64, device=dev), torch.empty(kept_cap, dtype=torch.int64, device=dev)
         t_k, alpha_c = torch.empty(kept_cap, dtype=torch.float32, device=dev), torch.empty(kept_cap, dtype=torch.float32, device=dev)
