@@ -99,6 +99,20 @@ def build_model(device, seed=42, radius=0.5, noise=2.0e-3, ln_inv_s_init=0.5298,
     return model
 
 
+def strong_shard(o, d, rank, world, total_rays, rays_per_rank, seed=None):
+    """The rays of ONE frame dealt to `world` ranks (strong scaling).  Image-ordered rays: row r of the frame -> rank r mod world (the ranks share
+    the object's rows; rays stay image-ordered inside a row); random pixels (`seed`): ray j of the draw -> rank j mod world.  Every ray goes to
+    exactly one rank."""
+    if seed is not None:
+        sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(seed))[:total_rays]
+        o, d = o[sel][rank::world], d[sel][rank::world]
+    elif total_rays == H * W and H % world == 0:
+        o, d = o.view(H, W, 3)[rank::world].reshape(-1, 3), d.view(H, W, 3)[rank::world].reshape(-1, 3)
+    else:
+        o, d = o[:total_rays][rank * rays_per_rank:(rank + 1) * rays_per_rank], d[:total_rays][rank * rays_per_rank:(rank + 1) * rays_per_rank]
+    return o.contiguous(), d.contiguous()
+
+
 def flat_grad_views(model):
     """One flat fp32 buffer holding every gradient (p.grad are views) -> a single all-reduce per step."""
     params = [p for p in model.parameters() if p.requires_grad]
@@ -554,15 +568,7 @@ def main():
         if args.scaling == "strong":           # ONE frame per step, its rows dealt to the ranks round-robin (row r -> rank r mod N): contiguous
             # blocks would give the ranks that own the object's rows most of the work (measured: 38 % efficiency at N = 8, profiles/r02s_*)
             o, d = pinhole_rays(H, W, orbit(k, N_VIEWS))
-            if args.random_rays:
-                sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(1000 + k))[:args.rays]
-                o, d = o[sel], d[sel]
-                o, d = o[rank::world], d[rank::world]
-            elif args.rays == H * W and H % world == 0:
-                o, d = o.view(H, W, 3)[rank::world].reshape(-1, 3), d.view(H, W, 3)[rank::world].reshape(-1, 3)
-            else:
-                o, d = o[:args.rays][rank * n_rays:(rank + 1) * n_rays], d[:args.rays][rank * n_rays:(rank + 1) * n_rays]
-            o, d = o.contiguous(), d.contiguous()
+            o, d = strong_shard(o, d, rank, world, args.rays, n_rays, seed=(1000 + k) if args.random_rays else None)
             if o.shape[0] < n_rays:                # the last rank's block is padded with its own last ray
                 pad = n_rays - o.shape[0]
                 o, d = torch.cat([o, o[-1:].expand(pad, 3)]).contiguous(), torch.cat([d, d[-1:].expand(pad, 3)]).contiguous()

@@ -31,6 +31,19 @@ def _worker(rank, world, port, out):
     dist.all_gather(gathered, local)
     assert torch.allclose(flat, sum(gathered), rtol=1e-6, atol=1e-7)
     assert torch.allclose(params[0].grad.flatten(), flat[:params[0].numel()])       # .grad are still views of the reduced buffer
+    # strong scaling: ONE frame dealt to the ranks by rows (round-robin) -- the shards partition the frame, equal sizes, rows stay whole
+    fo, fd = bench.pinhole_rays(bench.H, bench.W, bench.orbit(0, 8))
+    so, sd = bench.strong_shard(fo, fd, rank, world, bench.H * bench.W, bench.H * bench.W // world)
+    assert so.shape[0] == bench.H * bench.W // world
+    assert torch.equal(so.view(-1, bench.W, 3), fo.view(bench.H, bench.W, 3)[rank::world])
+    key = (sd * torch.tensor([1.0, 1e3, 1e6])).sum(-1).double()             # a fingerprint per ray direction
+    keys = [torch.zeros_like(key) for _ in range(world)]
+    dist.all_gather(keys, key)
+    allk = torch.cat(keys).sort().values
+    ref = (fd * torch.tensor([1.0, 1e3, 1e6])).sum(-1).double().sort().values
+    assert torch.equal(allk, ref)                                            # every ray of the frame exactly once over the ranks
+    ro_, rd_ = bench.strong_shard(fo, fd, rank, world, 4096, 4096 // world, seed=5)
+    assert ro_.shape[0] == 4096 // world
     if rank == 0:
         out.put((float(flat.abs().sum()), [float(g.abs().sum()) for g in gathered]))
     dist.barrier()
