@@ -587,6 +587,10 @@ k_color_rad_bwd(const ColorNetDev net, const uint8_t *__restrict__ Xt, const uin
 //   X1 += [dz | u]^T . [H | 1]   rows 0..63 = [dW1 (z part) | db1]
 //   X2 += [u | v]^T . [dG | 1]   rows 0..63, cols 0..31 = dW1 (second-order part);  rows 64..127, col 32 = dW2
 //   scatter per level / corner:  g_f * wsum_c(gin) + (dhz_f + dh_r_f) * w_c
+// TMA = true: the saved Z tile (16 KB) and the H half of the saved X tile (8 KB) are fetched by the bulk async copy engine into shared memory, and
+// the NEXT tile's fetch is issued right after the last MMA of the current tile -- it runs behind the whole scatter phase.  (Without it the two
+// epilogue loops read Z straight from global memory, 16 dependent round trips per tile at 8 warps per SM.)
+template <bool TMA>
 __global__ void __launch_bounds__(kTile)
 k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetDev net, const PointSrc ps, const uint8_t *__restrict__ Zt,
                 const uint8_t *__restrict__ Xt, const float *__restrict__ g_nab, const float *__restrict__ g_sdf, const float *__restrict__ dh_r,
@@ -601,9 +605,11 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
     uint8_t *sGe = sHe + kTile * NX * 2;                       // 12 KB [dG | 1 | 0]
     uint8_t *sW1 = sGe + kTile * NX * 2;                       //  4 KB
     uint8_t *sW1T = sW1 + HW * NF * 2;                         //  4 KB
+    uint8_t *sZ = sW1T + NF * HW * 2;                          // 16 KB saved pre-activations (TMA only)
     __shared__ float sW2[HW];
     __shared__ float sdb2;
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar_ld;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -620,6 +626,7 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
     if (tid == 0) {
         sdb2 = 0.f;
         tc::mbar_init(&mbar, 1);
+        tc::mbar_init(&mbar_ld, 1);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
@@ -634,10 +641,16 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     constexpr uint32_t cDU = 0, cG = 64, cDHZ = 96, cX1 = 128, cX2 = 176;
     const SoftplusK spk(net.beta);
-    uint32_t phase = 0;
+    uint32_t phase = 0, ld_phase = 0;
     bool first_tile = true;
 
     const int64_t n_tiles = (n + kTile - 1) / kTile;
+    auto fetch = [&](int64_t tile) {                          // one thread: Z tile + the H chunks of the X tile -> shared memory
+        tc::mbar_arrive_expect_tx(&mbar_ld, kTileBytes + 4 * kChunk);
+        tc::tma_load_bulk(sZ, Zt + tile * kTileBytes, kTileBytes, &mbar_ld);
+        tc::tma_load_bulk(sHe, Xt + tile * kTileBytes, 4 * kChunk, &mbar_ld);
+    };
+    if (TMA && tid == 0 && (int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * kTile + tid;
         const bool valid = i < n;
@@ -650,10 +663,16 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
             for (int d = 0; d < 3; ++d) gin[d] = g_nab[i * 3 + d] * net.fac[d] * 0.5f;
         }
         const float dsdf = (valid && g_sdf) ? g_sdf[i] : 0.f;
-        const uint8_t *zt = Zt + tile * kTileBytes, *xt = Xt + tile * kTileBytes;
+        const uint8_t *zt = TMA ? sZ : Zt + tile * kTileBytes;
+        if (TMA) {
+            tc::mbar_wait(&mbar_ld, ld_phase);                // this tile's Z and H have landed
+            ld_phase ^= 1;
+        } else {
+            const uint8_t *xt = Xt + tile * kTileBytes;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4 *>(sHe + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(xt + c * kChunk + tid * 16);
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4 *>(sHe + c * kChunk + tid * 16) = *reinterpret_cast<const uint4 *>(xt + c * kChunk + tid * 16);
+        }
         // u = fp16(w2 s)
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -741,6 +760,11 @@ k_color_sdf_bwd(const PLMeta m, const __half *__restrict__ grid, const ColorNetD
         tc::mbar_wait(&mbar, phase);
         phase ^= 1;
         tc::fence_after_sync();
+        if (TMA && tid == 0 && tile + gridDim.x < n_tiles) {
+            // sZ was last read by the threads before the __syncthreads that precedes the MMAs above, sHe by those MMAs, which have completed
+            tc::fence_async_smem();
+            fetch(tile + gridDim.x);
+        }
         // ---- merged scatter
 #pragma unroll 1
         for (uint32_t g4 = 0; g4 < 4; ++g4) {
@@ -891,10 +915,15 @@ extern "C" int nsb_fused_color_bwd(const nsb_lotd_meta *meta, const void *params
         if (int rc = check_launch("nsb_fused_color_bwd(radiance)")) return rc;
         dh = dh_scratch;
     }
-    constexpr int kSmemS = 3 * kTileBytes + 2 * kTile * 48 * 2 + 2 * HW * NF * 2 + 1024;
-    opt_in_smem(k_color_sdf_bwd, kSmemS);
+    constexpr int kSmemS = 3 * kTileBytes + 2 * kTile * 48 * 2 + 2 * HW * NF * 2 + kTileBytes + 1024;      // 97 KB: still 2 CTAs / SM (TMEM-bound anyway)
+    opt_in_smem(k_color_sdf_bwd<true>, kSmemS);
+    opt_in_smem(k_color_sdf_bwd<false>, kSmemS);
     PointSrc ps{x, rays_o, rays_d, t, ridx};
-    k_color_sdf_bwd<<<tiles_grid(n, 2), kTile, kSmemS, s>>>(m, (const __half *)params_half, d, ps, (const uint8_t *)act_z, (const uint8_t *)act_x, g_nablas,
-                                                            g_sdf, dh, n, max_level < 0 ? -1 : max_level, d_grid, d_W1, d_b1, d_W2, d_b2, dn.a);
+    if (g_opt_color_tma.load() >= 2)
+        k_color_sdf_bwd<true><<<tiles_grid(n, 2), kTile, kSmemS, s>>>(m, (const __half *)params_half, d, ps, (const uint8_t *)act_z, (const uint8_t *)act_x,
+                                                                      g_nablas, g_sdf, dh, n, max_level < 0 ? -1 : max_level, d_grid, d_W1, d_b1, d_W2, d_b2, dn.a);
+    else
+        k_color_sdf_bwd<false><<<tiles_grid(n, 2), kTile, kSmemS, s>>>(m, (const __half *)params_half, d, ps, (const uint8_t *)act_z, (const uint8_t *)act_x,
+                                                                       g_nablas, g_sdf, dh, n, max_level < 0 ? -1 : max_level, d_grid, d_W1, d_b1, d_W2, d_b2, dn.a);
     return check_launch("nsb_fused_color_bwd(sdf)");
 }

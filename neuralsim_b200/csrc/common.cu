@@ -19,7 +19,7 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace nsb
 
-namespace nsb { std::atomic<int> g_opt_sdf_simt{0}; std::atomic<int> g_opt_color_tma{1}; }
+namespace nsb { std::atomic<int> g_opt_sdf_simt{0}; std::atomic<int> g_opt_color_tma{2}; }
 
 namespace nsb {
 static thread_local DevCounts g_counts{nullptr, nullptr};
