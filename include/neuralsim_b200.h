@@ -53,7 +53,8 @@ const char *nsb_last_error(void);
 int nsb_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
 uint64_t nsb_launch_count(void);
-/* Self-check switches: key "sdf_simt" (0|1) routes nsb_fused_sdf* through the CUDA-core cross-check kernel. */
+/* Self-check / A-B switches: key "sdf_simt" (0|1) routes nsb_fused_sdf* through the CUDA-core cross-check kernel; "color_tma" (0|1|2) the
+ * TMA fetch of the saved activation tiles in the colour backward; "asm_chunk" (1|8) rays per search of the hit list in nsb_assemble_boundary. */
 int nsb_set_option(const char *key, int value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -110,6 +111,17 @@ int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, const float *ra
                             const uint8_t *grid_binary, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
                             const int32_t *packed_info, int32_t *num_steps, float *t_starts, float *t_ends, int32_t *ridx,
                             int32_t *gidx, int32_t *bidx, const int64_t *ray_list, int64_t n_list, const uint32_t *grid_bits, void *stream);
+/* Small batches (the time of a march is the latency of its longest ray, and the reference pays it twice, ray_marching.cu:179-241): the
+ * first round of the single-grid march that ALSO records sample k of ray i at rec_t[i * max_steps + k] (t_start), and the copy that
+ * replaces the second round: for the listed rays j < n_list (ray_list == NULL: every ray), i = ray_list[j],
+ * (first, n) = packed_info[i]: t_starts[first + k] = rec_t[i * max_steps + k], ridx[first + k] = i.  Same values as the two-round
+ * march bit for bit (the same arithmetic, run once).  Both count-aware (nsb_bind_device_counts: the rays / the listed rays). */
+int nsb_ray_marching_record(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
+                            const float *roi, int32_t rx, int32_t ry, int32_t rz, const uint8_t *grid_binary, float step_size,
+                            float max_step_size, float dt_gamma, uint32_t max_steps, int32_t *num_steps, float *rec_t,
+                            const uint32_t *grid_bits, void *stream);
+int nsb_march_compact(const float *rec_t, uint32_t max_steps, const int32_t *packed_info, const int64_t *ray_list, int64_t n_list,
+                      float *t_starts, int32_t *ridx, void *stream);
 /* words[(cells + 31) / 32]: the bool grid packed 32 cells per word (bit k of word w = cell 32 w + k).  Passing it as `grid_bits`
  * (single-grid marching only) saves every CTA the re-packing of the 64^3 grid into shared memory. */
 int nsb_pack_occ_bits(const uint8_t *grid_binary, int64_t cells, uint32_t *words, void *stream);
@@ -230,7 +242,7 @@ int nsb_fused_sdf_bwd_indexed(const nsb_lotd_meta *meta_host, const void *params
  * count-aware entry point of that thread consumes (and clears) the binding and its kernel processes min(n_arg, *c0) items -- n_arg
  * (the `n` / `n_packs` / `n_rays` / `n_list` argument) then is the CAPACITY the buffers and the grid were sized for.  c1 is the second
  * count of nsb_assemble_boundary (n_hit).  Count-aware: nsb_gather_rays, nsb_ray_marching_listed (first round: num_steps of the rays
- * in [*c0, n_rays) is written as 0; second round: the listed rays), nsb_fused_sdf_collect / _rays / _packs, nsb_fused_sdf_bwd(_indexed),
+ * in [*c0, n_rays) is written as 0; second round: the listed rays), nsb_ray_marching_record / nsb_march_compact (the same), nsb_fused_sdf_collect / _rays / _packs, nsb_fused_sdf_bwd(_indexed),
  * nsb_neus_upsample_cdf, nsb_packed_invert_cdf_shared_u, nsb_merge_sorted_vals, nsb_assemble_boundary, nsb_neus_alpha_forward
  * (num_steps of the packs in [*c0, n_packs) is written as 0) / _backward, nsb_compact_samples, nsb_scatter_f32, nsb_flag_nonzero,
  * nsb_fused_color_fwd / _bwd, nsb_composite_forward / _backward.  With every size on the device a whole fwd+bwd step has no host

@@ -29,6 +29,8 @@ struct MarchArgs {
     const uint32_t *grid_bits;     // optional: the grid already packed 32 cells / word (nsb_pack_occ_bits), copied instead of re-packed per CTA
     const int64_t *n_dev;          // optional device-resident count (nsb_bind_device_counts): of the rays (first round: num_steps of the rays
                                    // between it and n_rays is written as 0) or of the listed rays (second round)
+    float *rec_t;                  // REC only (first round): sample k of ray i is also recorded at rec_t[i max_steps + k], so that the second
+                                   // march of a small batch (latency of the longest ray, twice) becomes a copy (k_march_compact)
 };
 
 __device__ __forceinline__ float calc_dt(float t, float dt_gamma, float dt_min, float dt_max) {
@@ -44,7 +46,7 @@ __device__ __forceinline__ float next_axis(float unit, float dir, float inv_dir,
     return __fmul_rn(__fdiv_rn(__fmul_rn(d, inv_dir), r), extent);
 }
 
-template <bool SMEM_BITS>
+template <bool SMEM_BITS, bool REC = false>
 __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
     extern __shared__ uint32_t s_bits[];
     const int64_t cells = (int64_t)a.rx * a.ry * a.rz;
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
                     a.ridx[base + j] = (int32_t)i;
                     if (a.gidx) a.gidx[base + j] = gi;
                     if (a.bidx) a.bidx[base + j] = b;
+                } else if (REC) {
+                    a.rec_t[i * (int64_t)a.max_steps + j] = t0;
                 }
                 ++j;
                 t0 = t1;
@@ -145,6 +149,25 @@ __global__ void __launch_bounds__(256) k_ray_marching(const MarchArgs a) {
             }
         }
         if (first_round) a.num_steps[i] = (int32_t)j;
+    }
+}
+
+// Second round of a recorded march: sample k of listed ray j -> slot first + k of the packed arrays.  One warp per ray.
+__global__ void __launch_bounds__(256) k_march_compact(const float *__restrict__ rec_t, uint32_t max_steps, const int32_t *__restrict__ packed_info,
+                                                       const int64_t *__restrict__ ray_list, int64_t n_list, const int64_t *__restrict__ n_dev,
+                                                       float *__restrict__ t_starts, int32_t *__restrict__ ridx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_live = eff_n(n_list, n_dev);
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_live; j += nw) {
+        const int64_t i = ray_list ? ray_list[j] : j;
+        const int64_t first = packed_info[i * 2];
+        const int32_t cnt = packed_info[i * 2 + 1];
+        const float *src = rec_t + i * (int64_t)max_steps;
+        for (int32_t k = lane; k < cnt; k += 32) {
+            t_starts[first + k] = src[k];
+            ridx[first + k] = (int32_t)i;
+        }
     }
 }
 
@@ -195,7 +218,7 @@ extern "C" int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, cons
     if (packed_info == nullptr) NSB_REQUIRE(num_steps && !ray_list, "nsb_ray_marching: first round needs num_steps (and marches every ray)");
     else NSB_REQUIRE(t_starts && ridx, "nsb_ray_marching: second round needs t_starts and ridx (t_ends / gidx / bidx are optional)");
     MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, batch_inds, rx, ry, rz, grid_binary, step_size, max_step_size,
-                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, ray_list, n_list, grid_bits, dn.a};
+                dt_gamma, max_steps, packed_info, num_steps, t_starts, t_ends, ridx, gidx, bidx, ray_list, n_list, grid_bits, dn.a, nullptr};
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cells = (int64_t)rx * ry * rz;
     const size_t smem = (size_t)((cells + 31) / 32) * 4;
@@ -208,4 +231,34 @@ extern "C" int nsb_ray_marching_listed(int64_t n_rays, const float *rays_o, cons
         k_ray_marching<false><<<grid, 256, 0, s>>>(a);
     }
     return check_launch("nsb_ray_marching");
+}
+
+extern "C" int nsb_ray_marching_record(int64_t n_rays, const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
+                                       const float *roi, int32_t rx, int32_t ry, int32_t rz, const uint8_t *grid_binary, float step_size,
+                                       float max_step_size, float dt_gamma, uint32_t max_steps, int32_t *num_steps, float *rec_t,
+                                       const uint32_t *grid_bits, void *stream) {
+    const DevCounts dn = take_counts();
+    if (n_rays == 0) return 0;
+    NSB_REQUIRE(rays_o && rays_d && t_min && t_max && roi && grid_binary && num_steps && rec_t, "nsb_ray_marching_record: NULL argument");
+    NSB_REQUIRE(rx > 0 && ry > 0 && rz > 0 && max_steps > 0, "nsb_ray_marching_record: bad grid resolution / max_steps");
+    MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, nullptr, rx, ry, rz, grid_binary, step_size, max_step_size, dt_gamma, max_steps,
+                nullptr, num_steps, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, grid_bits, dn.a, rec_t};
+    const size_t smem = (size_t)(((int64_t)rx * ry * rz + 31) / 32) * 4;
+    const unsigned grid = wave_grid(n_rays, 256, 2);
+    if (smem <= 96 * 1024) {
+        opt_in_smem(k_ray_marching<true, true>, 96 * 1024);
+        k_ray_marching<true, true><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        k_ray_marching<false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    }
+    return check_launch("nsb_ray_marching_record");
+}
+
+extern "C" int nsb_march_compact(const float *rec_t, uint32_t max_steps, const int32_t *packed_info, const int64_t *ray_list, int64_t n_list,
+                                 float *t_starts, int32_t *ridx, void *stream) {
+    const DevCounts dn = take_counts();
+    if (n_list == 0) return 0;
+    NSB_REQUIRE(rec_t && packed_info && t_starts && ridx && max_steps > 0, "nsb_march_compact: NULL argument");
+    k_march_compact<<<wave_grid(n_list * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(rec_t, max_steps, packed_info, ray_list, n_list, dn.a, t_starts, ridx);
+    return check_launch("nsb_march_compact");
 }

@@ -193,7 +193,7 @@ k_merge_vals(const float *__restrict__ dep_a, const float *__restrict__ sdf_a, c
 // Ray r of the R tested rays carries nc coarse depths (sorted); if r == ridx_hit[j] it also carries the nf fine depths of
 // row j (a concatenation of sorted runs).  Output pack r = the sorted union; first_r = nc r + nf #{hit rays < r}.
 //   d1[first + k] = k-th smallest;  mid[first + k] = d1_k + (d1_{k+1} - d1_k) / 2 (last: + 0);  ridx_all = r.
-constexpr int kAsmWarps = 8, kAsmMaxRuns = 8;
+constexpr int kAsmWarps = 8, kAsmMaxRuns = 8, kAsmChunk = 8;
 struct AsmRuns { int n, len[kAsmMaxRuns]; };              // the fine row is a concatenation of `n` sorted runs (one per up-sampling stage)
 
 __device__ __forceinline__ int count_less(const float *a, int n, float v, bool or_equal) {   // #{a_i < v} or #{a_i <= v}, a sorted
@@ -206,59 +206,74 @@ __device__ __forceinline__ int count_less(const float *a, int n, float v, bool o
     return lo;
 }
 
+// CHUNK consecutive rays per warp trip: ONE search of the first ray in ridx_hit (18 dependent L2 loads on a frame -- half of the kernel's
+// time when every ray searched for itself, CHUNK = 1), the next CHUNK entries of the list in registers, a running rank for the rest.
+template <int CHUNK>
 __global__ void __launch_bounds__(kAsmWarps * 32)
 k_assemble_boundary(const float *__restrict__ coarse, int64_t n_rays, int nc, const int64_t *__restrict__ ridx_hit, int64_t n_hit,
                     const float *__restrict__ fine, int nf, const AsmRuns runs, float *__restrict__ d1, float *__restrict__ mid,
                     int64_t *__restrict__ ridx_all, int64_t *__restrict__ pack_infos, const int64_t *__restrict__ n_rays_dev,
                     const int64_t *__restrict__ n_hit_dev) {
     extern __shared__ float s_v[];                        // [warps][2][nc + nf]
+    static_assert(CHUNK >= 1 && CHUNK <= 32, "one candidate per lane");
     n_rays = eff_n(n_rays, n_rays_dev);
     n_hit = eff_n(n_hit, n_hit_dev);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, cap = nc + nf;
     float *raw = s_v + (size_t)w * 2 * cap, *srt = raw + cap;
-    for (int64_t r = gwarp_(); r < n_rays; r += nwarps_()) {
-        int64_t lo = 0, cnt = n_hit;                      // lower bound of r in ridx_hit
+    const int64_t n_chunks = (n_rays + CHUNK - 1) / CHUNK;
+    for (int64_t c = gwarp_(); c < n_chunks; c += nwarps_()) {
+        const int64_t r0 = c * CHUNK;
+        int64_t lo0 = 0, cnt = n_hit;                     // lower bound of r0 in ridx_hit
         while (cnt > 0) {
             const int64_t step = cnt >> 1;
-            if (ridx_hit[lo + step] < r) { lo += step + 1; cnt -= step + 1; } else cnt = step;
+            if (ridx_hit[lo0 + step] < r0) { lo0 += step + 1; cnt -= step + 1; } else cnt = step;
         }
-        const bool hit = lo < n_hit && ridx_hit[lo] == r;
-        const int n = nc + (hit ? nf : 0);
-        const int64_t first = (int64_t)nc * r + (int64_t)nf * lo;
-        if (lane == 0) { pack_infos[2 * r] = first; pack_infos[2 * r + 1] = n; }
-        if (!hit) {                                       // the coarse row is already sorted: straight copy
-            for (int k = lane; k < nc; k += 32) {
-                const float v = coarse[r * nc + k];
-                const float diff = (k < nc - 1) ? __fsub_rn(coarse[r * nc + k + 1], v) : 0.f;
+        long long cand = -1;                              // lane k: the k-th listed ray at or after r0
+        if (lane < CHUNK && lo0 + lane < n_hit) cand = ridx_hit[lo0 + lane];
+        int used = 0;                                     // listed rays among r0 .. r - 1
+        for (int j = 0; j < CHUNK; ++j) {
+            const int64_t r = r0 + j;
+            if (r >= n_rays) break;
+            const bool hit = __shfl_sync(0xffffffffu, cand, used) == r;      // used <= j < CHUNK
+            const int64_t lo = lo0 + used;
+            const int n = nc + (hit ? nf : 0);
+            const int64_t first = (int64_t)nc * r + (int64_t)nf * lo;
+            if (lane == 0) { pack_infos[2 * r] = first; pack_infos[2 * r + 1] = n; }
+            if (!hit) {                                   // the coarse row is already sorted: straight copy
+                for (int k = lane; k < nc; k += 32) {
+                    const float v = coarse[r * nc + k];
+                    const float diff = (k < nc - 1) ? __fsub_rn(coarse[r * nc + k + 1], v) : 0.f;
+                    d1[first + k] = v;
+                    mid[first + k] = __fadd_rn(v, __fmul_rn(diff, 0.5f));
+                    ridx_all[first + k] = r;
+                }
+                continue;
+            }
+            ++used;
+            __syncwarp();
+            for (int k = lane; k < nc; k += 32) raw[k] = coarse[r * nc + k];
+            for (int k = lane; k < nf; k += 32) raw[nc + k] = fine[lo * nf + k];
+            __syncwarp();
+            // stable rank of every element among the 1 + runs.n sorted runs: own index + (<=-count in earlier runs) + (<-count in later runs)
+            for (int e = lane; e < n; e += 32) {
+                const float v = raw[e];
+                int rank = 0, start = 0;
+                for (int q = -1; q < runs.n; ++q) {
+                    const int len = q < 0 ? nc : runs.len[q];
+                    if (e >= start && e < start + len) rank += e - start;
+                    else rank += count_less(raw + start, len, v, /*or_equal=*/start < e);
+                    start += len;
+                }
+                srt[rank] = v;
+            }
+            __syncwarp();
+            for (int k = lane; k < n; k += 32) {
+                const float v = srt[k];
+                const float diff = (k < n - 1) ? __fsub_rn(srt[k + 1], v) : 0.f;
                 d1[first + k] = v;
                 mid[first + k] = __fadd_rn(v, __fmul_rn(diff, 0.5f));
                 ridx_all[first + k] = r;
             }
-            continue;
-        }
-        __syncwarp();
-        for (int k = lane; k < nc; k += 32) raw[k] = coarse[r * nc + k];
-        for (int k = lane; k < nf; k += 32) raw[nc + k] = fine[lo * nf + k];
-        __syncwarp();
-        // stable rank of every element among the 1 + runs.n sorted runs: own index + (<=-count in earlier runs) + (<-count in later runs)
-        for (int e = lane; e < n; e += 32) {
-            const float v = raw[e];
-            int rank = 0, start = 0;
-            for (int q = -1; q < runs.n; ++q) {
-                const int len = q < 0 ? nc : runs.len[q];
-                if (e >= start && e < start + len) rank += e - start;
-                else rank += count_less(raw + start, len, v, /*or_equal=*/start < e);
-                start += len;
-            }
-            srt[rank] = v;
-        }
-        __syncwarp();
-        for (int k = lane; k < n; k += 32) {
-            const float v = srt[k];
-            const float diff = (k < n - 1) ? __fsub_rn(srt[k + 1], v) : 0.f;
-            d1[first + k] = v;
-            mid[first + k] = __fadd_rn(v, __fmul_rn(diff, 0.5f));
-            ridx_all[first + k] = r;
         }
     }
 }
@@ -418,6 +433,7 @@ __global__ void k_query_counts(int64_t *__restrict__ c, int phase, int nc, int n
 
 }  // namespace nsb
 
+namespace nsb { extern std::atomic<int> g_opt_asm_chunk; }
 using namespace nsb;
 #define STREAM ((cudaStream_t)stream)
 
@@ -479,7 +495,6 @@ extern "C" int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_
     NSB_REQUIRE(n_hit == 0 || (ridx_hit && fine), "nsb_assemble_boundary: hit rays need ridx_hit and fine");
     NSB_REQUIRE(n_coarse > 0 && n_fine >= 0 && n_coarse + n_fine <= 1024, "nsb_assemble_boundary: n_coarse + n_fine must be <= 1024");
     const size_t smem = (size_t)kAsmWarps * 2 * (n_coarse + n_fine) * sizeof(float);
-    opt_in_smem(k_assemble_boundary, 96 * 1024);
     NSB_REQUIRE(smem <= 96 * 1024, "nsb_assemble_boundary: too many samples per ray for shared memory");
     AsmRuns runs{};
     NSB_REQUIRE(n_runs >= 0 && n_runs <= kAsmMaxRuns && (n_runs == 0 || run_len), "nsb_assemble_boundary: at most %d sorted runs", kAsmMaxRuns);
@@ -487,8 +502,16 @@ extern "C" int nsb_assemble_boundary(const float *coarse, int64_t n_rays, int32_
     for (int q = 0; q < n_runs; ++q) { runs.len[q] = run_len[q]; tot += run_len[q]; }
     runs.n = n_runs;
     NSB_REQUIRE(tot == n_fine, "nsb_assemble_boundary: run lengths must add up to n_fine");
-    k_assemble_boundary<<<wave_grid(n_rays * 32, kAsmWarps * 32, 8), kAsmWarps * 32, smem, STREAM>>>(coarse, n_rays, n_coarse, ridx_hit, n_hit, fine, n_fine,
-                                                                                                  runs, d1, mid, ridx_all, pack_infos, dn.a, dn.b);
+    const unsigned grid = wave_grid(n_rays * 32, kAsmWarps * 32, 8);
+    if (g_opt_asm_chunk.load() > 1) {                     // rays per search of the hit list (nsb_set_option "asm_chunk": 1 = every ray searches, A/B)
+        opt_in_smem(k_assemble_boundary<kAsmChunk>, 96 * 1024);
+        k_assemble_boundary<kAsmChunk><<<grid, kAsmWarps * 32, smem, STREAM>>>(coarse, n_rays, n_coarse, ridx_hit, n_hit, fine, n_fine, runs, d1, mid, ridx_all,
+                                                                             pack_infos, dn.a, dn.b);
+    } else {
+        opt_in_smem(k_assemble_boundary<1>, 96 * 1024);
+        k_assemble_boundary<1><<<grid, kAsmWarps * 32, smem, STREAM>>>(coarse, n_rays, n_coarse, ridx_hit, n_hit, fine, n_fine, runs, d1, mid, ridx_all,
+                                                                     pack_infos, dn.a, dn.b);
+    }
     return check_launch("nsb_assemble_boundary");
 }
 

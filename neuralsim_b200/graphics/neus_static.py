@@ -15,6 +15,7 @@ tests/test_static_gpu.py: images bit-equal to the host-sized path, gradients equ
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -29,6 +30,16 @@ __all__ = ["render_static", "StaticFrame", "CNT_SLOTS"]
 CNT_SLOTS = dict(n_rays=0, pairs=2, marched_raw=3, hit_raw=4, kept_raw=6, kept_rays_raw=7, nonzero=9, marched=12, hit=13, fine0=14,
                  boundary=18, kept=19, overflow=20, kept_rays=21, merged0=22, rays_if_kept_fits=26)
 _NULL = ctypes.c_void_p(0)
+# "auto": small batches march once and copy (nsb_ray_marching_record + nsb_march_compact) when the per-ray record fits this many bytes;
+# "0": always the two-round march; "1": always the recorded march.  Same samples bit for bit either way.
+MARCH_ONEPASS = os.environ.get("NSB_MARCH_ONEPASS", "auto")
+MARCH_ONEPASS_MAX_BYTES = 64 << 20
+
+
+def march_onepass(n_rays, max_steps):
+    if MARCH_ONEPASS == "0":
+        return False
+    return MARCH_ONEPASS == "1" or 4 * int(n_rays) * int(max_steps) <= MARCH_ONEPASS_MAX_BYTES
 
 
 def _slot(cnt, k):
@@ -377,9 +388,16 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
         margs = (L.c_i64(R), P(o_c, "f32"), P(d_c, "f32"), P(n_c, "f32"), P(f_c, "f32"), P(roi, "f32"), None, L.c_i32(res[0]), L.c_i32(res[1]), L.c_i32(res[2]),
                  P(g8, "u8"), L.c_f32(step_size), L.c_f32(max_step_size), L.c_f32(dt_gamma), ctypes.c_uint32(max_steps))
         num_steps = torch.empty(R, dtype=torch.int32, device=dev)
+        # small batches: a march costs the latency of its longest ray -> march ONCE, recording the samples per ray, and copy (csrc/march.cu)
+        rec_t = torch.empty(R * max_steps, dtype=torch.float32, device=dev) if march_onepass(R, max_steps) else None
         with L.KERNEL_TIMER.time("march", R):
-            _call(lib.nsb_ray_marching_listed, "ray_marching", cnt, CNT_SLOTS["n_rays"], None, *margs, None, P(num_steps), None, None, None, None, None, None,
-                  L.c_i64(0), P(bits), L.stream_ptr())
+            if rec_t is not None:
+                _call(lib.nsb_ray_marching_record, "ray_marching_record", cnt, CNT_SLOTS["n_rays"], None, L.c_i64(R), P(o_c, "f32"), P(d_c, "f32"), P(n_c, "f32"),
+                      P(f_c, "f32"), P(roi, "f32"), L.c_i32(res[0]), L.c_i32(res[1]), L.c_i32(res[2]), P(g8, "u8"), L.c_f32(step_size), L.c_f32(max_step_size),
+                      L.c_f32(dt_gamma), ctypes.c_uint32(max_steps), P(num_steps), P(rec_t), P(bits), L.stream_ptr())
+            else:
+                _call(lib.nsb_ray_marching_listed, "ray_marching", cnt, CNT_SLOTS["n_rays"], None, *margs, None, P(num_steps), None, None, None, None, None, None,
+                      L.c_i64(0), P(bits), L.stream_ptr())
         info2 = torch.empty(R, 2, dtype=torch.int32, device=dev)
         ridx_hit = torch.empty(R, dtype=torch.int64, device=dev)
         pack_infos = torch.empty(R, 2, dtype=torch.int64, device=dev)
@@ -388,8 +406,12 @@ def render_static(model, rays_o, rays_d, rays_h_appear=None, *, near=None, far=N
         depth = torch.empty(march_cap, dtype=torch.float32, device=dev)
         ridx32 = torch.empty(march_cap, dtype=torch.int32, device=dev)
         with L.KERNEL_TIMER.time("march", R):
-            _call(lib.nsb_ray_marching_listed, "ray_marching", cnt, CNT_SLOTS["hit"], None, *margs, P(info2), None, P(depth), None, P(ridx32), None, None,
-                  P(ridx_hit, "i64"), L.c_i64(R), P(bits), L.stream_ptr())
+            if rec_t is not None:
+                _call(lib.nsb_march_compact, "march_compact", cnt, CNT_SLOTS["hit"], None, P(rec_t, "f32"), ctypes.c_uint32(max_steps), P(info2, "i32"),
+                      P(ridx_hit, "i64"), L.c_i64(R), P(depth), P(ridx32), L.stream_ptr())
+            else:
+                _call(lib.nsb_ray_marching_listed, "ray_marching", cnt, CNT_SLOTS["hit"], None, *margs, P(info2), None, P(depth), None, P(ridx32), None, None,
+                      P(ridx_hit, "i64"), L.c_i64(R), P(bits), L.stream_ptr())
         ridx = ridx32.long()
         # ---------------- up-sampling (no grad)
         from . import neus as GN

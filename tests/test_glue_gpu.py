@@ -53,11 +53,21 @@ def test_merge_sorted_vals_equals_aligned_merge():
         assert none is None and torch.equal(dep_m2, dep_ref)
 
 
-def test_assemble_boundary_equals_reference_chain():
+@pytest.fixture(params=[8, 1])
+def asm_chunk(request):
+    """both flavours of nsb_assemble_boundary: one search of the hit list per 8 rays (default) / per ray"""
+    import ctypes
+    from neuralsim_b200 import _lib as L
+    L.lib().nsb_set_option(b"asm_chunk", ctypes.c_int(request.param))
+    yield request.param
+    L.lib().nsb_set_option(b"asm_chunk", ctypes.c_int(8))
+
+
+def test_assemble_boundary_equals_reference_chain(asm_chunk):
     from neuralsim_b200.graphics import neus_fused as NF
     from neuralsim_b200.graphics.pack_ops import merge_two_batch_a_includes_b, packed_diff
     g = torch.Generator().manual_seed(2)
-    R, nc = 700, 65
+    R, nc = 701, 65
     near = torch.rand(R, generator=g) + 0.5
     coarse = (near[:, None] + torch.linspace(0, 1, nc)[None, :] * (1 + torch.rand(R, 1, generator=g))).cuda().contiguous()
     ridx_hit = torch.randperm(R, generator=g)[:260].sort().values.cuda()
@@ -82,6 +92,13 @@ def test_assemble_boundary_equals_reference_chain():
     assert torch.equal(d1s, d_ref)
     d1, mid, ridx_all, pi = NF.assemble_boundary(coarse, ridx_hit[:0], fine_all[:0])
     assert torch.equal(d1, coarse.flatten()) and torch.equal(pi[:, 1], torch.full((R,), nc, device="cuda"))
+    # every ray carries fine samples (runs of listed rays longer than a chunk), and only the last one does
+    fa = (coarse[:, :1] + torch.rand(R, 20, generator=g).sort(-1).values.cuda() * 1.5).contiguous()
+    d1, _, ridx_all, pi = NF.assemble_boundary(coarse, ridx_c, fa)
+    assert torch.equal(d1.view(R, nc + 20), torch.cat([coarse, fa], -1).sort(-1).values) and torch.equal(pi[:, 0], ridx_c * (nc + 20))
+    d1, _, ridx_all, pi = NF.assemble_boundary(coarse, ridx_c[-1:], fa[-1:].contiguous())
+    assert torch.equal(d1[:(R - 1) * nc], coarse[:-1].flatten()) and torch.equal(d1[(R - 1) * nc:], torch.cat([coarse[-1], fa[-1]]).sort().values)
+    assert int(pi[-1, 1]) == nc + 20 and bool((ridx_all[(R - 1) * nc:] == R - 1).all())
 
 
 def test_neus_alpha_compact_equals_compress_and_gathers():

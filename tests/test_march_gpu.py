@@ -62,3 +62,41 @@ def test_batched_bit_exact(cuda):
     assert torch.equal(info.cpu(), ref[0]) and torch.equal(ridx.cpu(), ref[3]) and torch.equal(gidx.cpu(), ref[4])
     assert torch.equal(bidx.cpu(), ref[5]) and torch.equal(t0.squeeze(-1).cpu(), ref[1])
     assert int(info[bi.to(cuda) < 0][:, 1].sum()) == 0                          # rays with batch_ind < 0 produce nothing
+
+
+@pytest.mark.parametrize("grid_kind", ["sphere", "random", "full"])
+def test_recorded_march_equals_two_rounds(cuda, grid_kind):
+    """nsb_ray_marching_record + nsb_march_compact (march once, copy) == the two-round march bit for bit, with the ray count on the device"""
+    import ctypes
+    from neuralsim_b200 import _lib as L
+    from neuralsim_b200.bindings import _occ_grid
+    o, d, near, far = (x.to(cuda) for x in _rays(2, 40, 56))
+    rng = np.random.default_rng(5)
+    grid = {"sphere": oscene.make_occ_grid(64), "random": torch.from_numpy(rng.random((32, 24, 40)) < 0.15),
+            "full": torch.ones(16, 16, 16, dtype=torch.bool)}[grid_kind].to(cuda)
+    roi = torch.tensor([-1., -1, -1, 1, 1, 1], device=cuda)
+    R, max_steps, n_live = o.shape[0], 192, o.shape[0] - 37
+    ref = _occ_grid.ray_marching(o[:n_live].contiguous(), d[:n_live].contiguous(), near[:n_live].contiguous(), far[:n_live].contiguous(), roi, grid,
+                                 _occ_grid.ContractionType.AABB, 0.005, 0.05, 0.0, max_steps, False)
+    lib, P = L.lib(), L.ptr
+    cnt = torch.tensor([n_live, 0], dtype=torch.int64, device=cuda)
+    num = torch.full((R,), -1, dtype=torch.int32, device=cuda)
+    rec = torch.full((R * max_steps,), float("nan"), device=cuda)
+    g8 = grid.contiguous().view(torch.uint8)
+    lib.nsb_bind_device_counts(ctypes.c_void_p(cnt.data_ptr()), None)
+    L.check(lib.nsb_ray_marching_record(L.c_i64(R), P(o.contiguous()), P(d.contiguous()), P(near), P(far), P(roi), L.c_i32(grid.shape[0]), L.c_i32(grid.shape[1]),
+                                        L.c_i32(grid.shape[2]), P(g8), L.c_f32(0.005), L.c_f32(0.05), L.c_f32(0.0), ctypes.c_uint32(max_steps), P(num), P(rec),
+                                        None, L.stream_ptr()), "record")
+    assert torch.equal(num[:n_live], ref[0][:, 1]) and int(num[n_live:].abs().sum()) == 0
+    info2 = torch.stack([num.cumsum(0, dtype=torch.int32) - num, num], -1).contiguous()
+    hit = torch.nonzero(num).flatten().contiguous()
+    M = int(num.sum())
+    assert M == ref[1].shape[0] and M > 0
+    t, ridx = torch.full((M + 8,), -7.0, device=cuda), torch.full((M + 8,), -7, dtype=torch.int32, device=cuda)
+    cnt[1] = hit.numel()
+    lib.nsb_bind_device_counts(ctypes.c_void_p(cnt.data_ptr() + 8), None)
+    L.check(lib.nsb_march_compact(P(rec), ctypes.c_uint32(max_steps), P(info2), P(hit), L.c_i64(R), P(t), P(ridx), L.stream_ptr()), "compact")
+    assert torch.equal(t[:M], ref[1].squeeze(-1)) and torch.equal(ridx[:M], ref[3])
+    assert bool((t[M:] == -7.0).all()) and bool((ridx[M:] == -7).all())                     # nothing beyond the packed samples
+    if grid_kind == "full":
+        assert int(num.max()) == max_steps
