@@ -610,6 +610,10 @@ class StaticFrame:
         if not self.use_graph:
             self.graph = None
             return self
+        if not bool(self.rays_d.any()):
+            # the warm-up and the capture RUN the step on the input buffers; a zero direction never leaves the marcher's voxel-skipping loop
+            # (the reference's kernel has the same loop, occ_grid/helpers_march.h:58-69) -- refuse instead of hanging the device
+            raise RuntimeError("StaticFrame.capture: the input buffers hold no rays yet; call step(rays_o, rays_d, ...) or fill frame.rays_o / frame.rays_d first")
         was = L.KERNEL_TIMER.enabled
         L.KERNEL_TIMER.enabled = False                      # events cannot be recorded into a capture
         import gc

@@ -1,6 +1,8 @@
 """A/B of the step's glue on one B200, one process, same model and poses (not a bench value; bench.py is):
    asm_chunk   1 = every ray of nsb_assemble_boundary searches the hit list, 8 = one search per 8 consecutive rays
    onepass     0 = two-round march, 1 = march once recording the samples per ray + copy (auto: only when the record fits 64 MB)
+(r02j: the first version of this script captured its second frame with all-zero input rays and hung in the march until its timeout; only the
+first configuration of each run was recorded, profiles/r02j_ab_old_config.jsonl.  Fixed below, not re-run: no GPU time was left.)
 Usage: python profiles/ab_glue.py [--rays 480000 | --rays 4096 --random-rays] [--steps 20] [--rounds 2]"""
 import argparse
 import ctypes
@@ -50,6 +52,7 @@ def main():
                 fr.rays_o.copy_(o); fr.rays_d.copy_(d)
                 fr._size()
             caps.update(march_cap=fr.march_cap, kept_cap=fr.kept_cap, coherent=fr.coherent)
+        fr.rays_o.copy_(views[0][0]); fr.rays_d.copy_(views[0][1])     # the capture's warm-up must see real rays (all-zero directions march forever)
         fr.capture()
         for i in range(args.warmup):
             fr.step(*views[i % len(views)])
@@ -63,7 +66,7 @@ def main():
         torch.cuda.synchronize()
         ts = sorted(a.elapsed_time(b) for a, b in evs)
         assert fr.counts()["overflow"] == 0
-        chk = float(fr.rendered["rgb_volume"].double().sum()), float(fr.rendered["depth_volume"].double().sum())
+        chk = float(fr.rendered["rgb_volume"].detach().double().sum()), float(fr.rendered["depth_volume"].detach().double().sum())
         del fr
         gc.collect()
         torch.cuda.empty_cache()
