@@ -43,3 +43,27 @@ def test_bench_line_files_are_valid_json():
             for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "higher_is_better", "scaling", "e2e", "gpu_launches", "roofline", "config"):
                 assert k in d, (name, k)
             assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+
+
+def test_march_onepass_gate_and_final_bench_line():
+    """the recorded one-pass march is a small-batch path (record <= 64 MB unless forced); the last round-2 bench line keeps the contract's keys"""
+    import json
+    from neuralsim_b200.graphics import neus_static as NS
+    old = NS.MARCH_ONEPASS
+    try:
+        NS.MARCH_ONEPASS = "auto"
+        assert NS.march_onepass(4096, 1024) and NS.march_onepass(16384, 1024) and not NS.march_onepass(480000, 1024)
+        NS.MARCH_ONEPASS = "0"
+        assert not NS.march_onepass(16, 16)
+        NS.MARCH_ONEPASS = "1"
+        assert NS.march_onepass(480000, 1024)
+    finally:
+        NS.MARCH_ONEPASS = old
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02j_bench.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "e2e", "gpu_launches",
+              "roofline", "cpu_baseline", "clocks", "median"):
+        assert k in d, k
+    assert d["config"]["workload"] == "cfg2" and d["e2e"]["d2h_bytes_per_step"] > 15_000_000 and d["e2e"]["value"] < d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is not None
+    assert not d["clocks"]["reasons"] and d["step_ms"]["resident_stats"]["max"] / d["step_ms"]["resident_stats"]["median"] <= 1.15
